@@ -1,0 +1,398 @@
+// Ensemble-smoother analysis on sm_100a: ES, localised ES, IES step, taper.
+//
+// Replaces ens_update0 / ens_update0_loc / the IES loop body
+// (HistoryMatch.py:578-586, 774-797, 927-942) and
+// loc.bump(loc.pairwise_distances(...)) (tools/localization.py:9-92).
+// Big products go through the DMMA GEMM (hm_gemm.cu); the p x p / N x N
+// factorisations use cuSOLVER (a library call); the
+// per-parameter local analyses are a hand-written batched Cholesky in shared
+// memory, one CTA per parameter.
+//
+// Algebra used (all exact rewrites of the reference expressions):
+//  * S = center(Eo) decorr has zero column sums, so S^T X = S^T E: the
+//    parameter ensemble never needs centring.
+//  * C = S^T S + (N-1) I is SPD with eigenvalues >= N-1, so pinv(C) = C^-1
+//    and a Cholesky solve replaces the SVD pseudo-inverse.
+//  * ES is evaluated as E + (D C^-1)(S^T E): 4 N p M flops instead of the
+//    reference's left-to-right 2 N^2 M.
+#include "hm_common.cuh"
+
+namespace hm {
+int dgemm(hm_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_t k, double alpha,
+          const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C,
+          int64_t ldc);
+}
+
+namespace {
+
+int ensure_solver(hm_ctx* ctx) {
+    if (!ctx->solver) {
+        HM_CUSOLVER(cusolverDnCreate(&ctx->solver));
+        HM_CUSOLVER(cusolverDnSetStream(ctx->solver, ctx->stream));
+    }
+    return HM_OK;
+}
+
+// ---- column means / anomalies (utils.center, tools/utils.py:10-28) -----------------------------
+// One thread per column, coalesced across columns; rows are split over
+// blockIdx.y slabs only for the mean pass when N is large.
+__global__ void k_col_mean(int64_t N, int64_t M, const double* __restrict__ E, int64_t ldE,
+                           double* __restrict__ mean) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    double s = 0.0;
+    for (int64_t i = 0; i < N; ++i) s += E[i * ldE + j];
+    mean[j] = s / (double)N;
+}
+__global__ void k_sub_mean(int64_t N, int64_t M, const double* __restrict__ E, int64_t ldE,
+                           double* __restrict__ X, int64_t ldX, const double* __restrict__ mean,
+                           double scale) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = blockIdx.y;
+    if (j >= M) return;
+    X[i * ldX + j] = (E[i * ldE + j] - mean[j]) * scale;
+}
+
+// D0 = obs - Eo - perturbs (HistoryMatch.py:584)
+__global__ void k_innovation(int64_t N, int64_t p, const double* __restrict__ obs,
+                             const double* __restrict__ Eo, const double* __restrict__ pert,
+                             double* __restrict__ D0) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * p) return;
+    D0[i] = obs[i % p] - Eo[i] - pert[i];
+}
+
+__global__ void k_add_diag(int64_t n, double* __restrict__ A, int64_t lda, double v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A[i * lda + i] += v;
+}
+
+// out = a*X + b*I - c*W  style helpers for the IES step
+__global__ void k_ies_grad_b(int64_t N, double* __restrict__ G, const double* __restrict__ W,
+                             double nm1) {
+    // G += (N-1) (I - W)
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * N) return;
+    const int64_t r = i / N, c = i % N;
+    G[i] += nm1 * ((r == c ? 1.0 : 0.0) - W[i]);
+}
+__global__ void k_axpy(int64_t n, double a, const double* __restrict__ x, double* __restrict__ y) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = fma(a, x[i], y[i]);
+}
+__global__ void k_ies_resid(int64_t N, int64_t p, const double* __restrict__ y,
+                            const double* __restrict__ Dp, const double* __restrict__ Eow,
+                            double* __restrict__ out) {
+    // out = y - Dp - Eo_w
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * p) return;
+    out[i] = y[i % p] - Dp[i] - Eow[i];
+}
+__global__ void k_set_identity(int64_t n, double* __restrict__ A) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * n) return;
+    A[i] = (i / n == i % n) ? 1.0 : 0.0;
+}
+
+// ---- taper (tools/localization.py:9-92) ----------------------------------------------------------
+__global__ void k_taper_bump(int64_t M, int64_t p, const double* __restrict__ xy_prm,
+                             const double* __restrict__ xy_obs, double radius, double sharp,
+                             double* __restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * p) return;
+    const int64_t i = idx / p, j = idx % p;
+    const double dx = xy_prm[2 * i] - xy_obs[2 * j], dy = xy_prm[2 * i + 1] - xy_obs[2 * j + 1];
+    const double x = sqrt(dx * dx + dy * dy) / radius;
+    double v = 0.0;
+    if (fabs(x) < 1.0) {
+        v = exp(1.0 - 1.0 / (1.0 - x * x));
+        if (sharp != 1.0) v = pow(v, sharp);
+    }
+    out[idx] = v;
+}
+
+// ---- batched local analysis (HistoryMatch.py:783-793) ----------------------------------------
+// One CTA per parameter i.  Inputs: A = S^T S (p,p), B = S^T E (p,M) whose
+// column i is this parameter's right-hand side.  Builds the tapered system
+// Ci = (c c^T) o A[jj,jj] + (N-1) I on the active observations jj
+// (sqrt(taper) > 1e-2), Cholesky-factorises it in shared memory, solves and
+// writes w~ = c o Ci^-1 (c o B[jj,i]) back into column i of B (zeros on
+// inactive rows), so that the caller finishes with E += D B.
+__global__ void __launch_bounds__(256)
+k_local_analysis(int64_t M, int p, double nm1, const double* __restrict__ A,
+                 const double* __restrict__ taper, double* __restrict__ B, int64_t ldB,
+                 int* __restrict__ fail) {
+    extern __shared__ double sm[];
+    const int64_t i = blockIdx.x;
+    double* c = sm;           // [p] sqrt(taper) of active obs
+    double* rhs = sm + p;     // [p]
+    int* idx = (int*)(sm + 2 * p);  // [p] active obs indices
+    double* L = sm + 2 * p + (p + 1) / 2;  // [pi][pi] row-major, lower triangle
+    __shared__ int s_n;
+    __shared__ int s_fail;
+    const int tid = threadIdx.x, nt = blockDim.x;
+
+    // ordered compaction of the active set (ascending j, like boolean indexing)
+    if (tid == 0) {
+        int n = 0;
+        for (int j = 0; j < p; ++j) {
+            const double cj = sqrt(taper[i * p + j]);
+            if (cj > 1e-2) {
+                idx[n] = j;
+                c[n] = cj;
+                ++n;
+            }
+        }
+        s_n = n;
+        s_fail = 0;
+    }
+    __syncthreads();
+    const int n = s_n;
+    for (int a = tid; a < n; a += nt) rhs[a] = c[a] * B[(int64_t)idx[a] * ldB + i];
+    for (int e = tid; e < n * n; e += nt) {
+        const int a = e / n, b = e % n;
+        if (b <= a) L[a * n + b] = c[a] * c[b] * A[(int64_t)idx[a] * p + idx[b]] + (a == b ? nm1 : 0.0);
+    }
+    __syncthreads();
+    // right-looking Cholesky
+    for (int k = 0; k < n; ++k) {
+        const double dkk = L[k * n + k];
+        if (tid == 0 && !(dkk > 0.0)) s_fail = 1;
+        const double d = sqrt(dkk);
+        __syncthreads();
+        for (int a = k + tid; a < n; a += nt) L[a * n + k] = (a == k) ? d : L[a * n + k] / d;
+        __syncthreads();
+        const int rem = n - k - 1;
+        for (int e = tid; e < rem * rem; e += nt) {
+            const int a = k + 1 + e / rem, b = k + 1 + e % rem;
+            if (b <= a) L[a * n + b] -= L[a * n + k] * L[b * n + k];
+        }
+        __syncthreads();
+    }
+    // forward / backward substitution (warp 0; columns processed in order)
+    if (tid < 32) {
+        for (int k = 0; k < n; ++k) {
+            const double yk = rhs[k] / L[k * n + k];
+            __syncwarp();
+            if (tid == 0) rhs[k] = yk;
+            for (int a = k + 1 + tid; a < n; a += 32) rhs[a] -= L[a * n + k] * yk;
+            __syncwarp();
+        }
+        for (int k = n - 1; k >= 0; --k) {
+            const double wk = rhs[k] / L[k * n + k];
+            __syncwarp();
+            if (tid == 0) rhs[k] = wk;
+            for (int a = tid; a < k; a += 32) rhs[a] -= L[k * n + a] * wk;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < p; j += nt) B[(int64_t)j * ldB + i] = 0.0;
+    __syncthreads();
+    for (int a = tid; a < n; a += nt) B[(int64_t)idx[a] * ldB + i] = c[a] * rhs[a];
+    if (tid == 0 && s_fail) atomicExch(fail, 1);
+}
+
+// S = center(Eo) decorr, D = (obs - Eo - perturbs) decorr (HistoryMatch.py:580-584)
+int whiten(hm_ctx* ctx, int64_t N, int64_t p, const double* Eo, const double* obs,
+           const double* perturbs, const double* decorr, double** S_out, double** D_out) {
+    cudaStream_t st = ctx->stream;
+    double *tmp, *mean, *S, *D;
+    HM_CHECK(ctx->ws.get("an.tmp", (size_t)N * p, &tmp));
+    HM_CHECK(ctx->ws.get("an.mean", (size_t)p, &mean));
+    HM_CHECK(ctx->ws.get("an.S", (size_t)N * p, &S));
+    HM_CHECK(ctx->ws.get("an.D", (size_t)N * p, &D));
+    const int tb = 128;
+    k_col_mean<<<(unsigned)((p + tb - 1) / tb), tb, 0, st>>>(N, p, Eo, p, mean);
+    k_sub_mean<<<dim3((unsigned)((p + tb - 1) / tb), (unsigned)N), tb, 0, st>>>(N, p, Eo, p, tmp, p, mean, 1.0);
+    HM_CHECK(hm::dgemm(ctx, false, false, N, p, p, 1.0, tmp, p, decorr, p, 0.0, S, p));
+    k_innovation<<<(unsigned)((N * p + 255) / 256), 256, 0, st>>>(N, p, obs, Eo, perturbs, tmp);
+    HM_CHECK(hm::dgemm(ctx, false, false, N, p, p, 1.0, tmp, p, decorr, p, 0.0, D, p));
+    *S_out = S;
+    *D_out = D;
+    return HM_OK;
+}
+
+int check_info(hm_ctx* ctx, int* d_info, const char* what) {
+    HM_CUDA(cudaMemcpyAsync(ctx->h_pinned, d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    HM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_pinned[0] != 0) {
+        hm::set_error("%s failed: info = %d", what, ctx->h_pinned[0]);
+        return HM_ERR_NUMERIC;
+    }
+    return HM_OK;
+}
+
+// Cholesky factor of the SPD n x n matrix A (row-major == column-major by symmetry), in place.
+int chol_factor(hm_ctx* ctx, int n, double* A) {
+    HM_CHECK(ensure_solver(ctx));
+    int lwork = 0;
+    HM_CUSOLVER(cusolverDnDpotrf_bufferSize(ctx->solver, CUBLAS_FILL_MODE_LOWER, n, A, n, &lwork));
+    double* work;
+    int* info;
+    HM_CHECK(ctx->ws.get("an.potrf_work", (size_t)std::max(lwork, 1), &work));
+    HM_CHECK(ctx->ws.get("an.info", (size_t)4, &info));
+    HM_CUSOLVER(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, n, A, n, work, lwork, info));
+    return check_info(ctx, info, "Cholesky factorisation (potrf)");
+}
+// In place: Brow (nrhs x n, row-major) <- Brow A^-1, using the factor from chol_factor.
+// (column-major view of Brow is n x nrhs = Brow^T, and A^-1 Brow^T = (Brow A^-1)^T.)
+int chol_solve_right(hm_ctx* ctx, int n, const double* Afac, int nrhs, double* Brow) {
+    int* info;
+    HM_CHECK(ctx->ws.get("an.info", (size_t)4, &info));
+    HM_CUSOLVER(cusolverDnDpotrs(ctx->solver, CUBLAS_FILL_MODE_LOWER, n, nrhs, Afac, n, Brow, n, info));
+    return check_info(ctx, info, "Cholesky solve (potrs)");
+}
+
+}  // namespace
+
+extern "C" int hm_center(hm_ctx* ctx, int64_t N, int64_t M, const double* E, int64_t ldE, double* X,
+                         int64_t ldX, double* mean, int rescale) {
+    HM_REQUIRE(ctx && E && X, "null pointer");
+    HM_REQUIRE(N > 0 && M > 0, "empty ensemble");
+    HM_CUDA(cudaSetDevice(ctx->device));
+    double* mu = mean;
+    if (!mu) HM_CHECK(ctx->ws.get("an.center_mean", (size_t)M, &mu));
+    const int tb = 128;
+    const unsigned gx = (unsigned)((M + tb - 1) / tb);
+    k_col_mean<<<gx, tb, 0, ctx->stream>>>(N, M, E, ldE, mu);
+    const double scale = (rescale && N > 1) ? sqrt((double)N / (double)(N - 1)) : 1.0;
+    k_sub_mean<<<dim3(gx, (unsigned)N), tb, 0, ctx->stream>>>(N, M, E, ldE, X, ldX, mu, scale);
+    HM_CUDA(cudaGetLastError());
+    return HM_OK;
+}
+
+extern "C" int hm_taper_bump(hm_ctx* ctx, int64_t M, int64_t p, const double* xy_prm,
+                             const double* xy_obs, double radius, double sharpness, double* out) {
+    HM_REQUIRE(ctx && xy_prm && xy_obs && out, "null pointer");
+    HM_REQUIRE(radius > 0, "radius > 0");
+    HM_CUDA(cudaSetDevice(ctx->device));
+    k_taper_bump<<<(unsigned)((M * p + 255) / 256), 256, 0, ctx->stream>>>(M, p, xy_prm, xy_obs, radius,
+                                                                            sharpness, out);
+    HM_CUDA(cudaGetLastError());
+    return HM_OK;
+}
+
+extern "C" int hm_es_update(hm_ctx* ctx, int64_t N, int64_t M, int64_t p, double* E, int64_t ldE,
+                            const double* Eo, const double* obs, const double* perturbs,
+                            const double* decorr) {
+    HM_REQUIRE(ctx && E && Eo && obs && perturbs && decorr, "null pointer");
+    HM_REQUIRE(N > 1 && M > 0 && p > 0 && ldE >= M, "shape");
+    HM_CUDA(cudaSetDevice(ctx->device));
+    double *S, *D, *C, *G;
+    HM_CHECK(whiten(ctx, N, p, Eo, obs, perturbs, decorr, &S, &D));
+    HM_CHECK(ctx->ws.get("an.C", (size_t)p * p, &C));
+    HM_CHECK(ctx->ws.get("an.G", (size_t)p * M, &G));
+    // C = S^T S + (N-1) I
+    HM_CHECK(hm::dgemm(ctx, true, false, p, p, N, 1.0, S, p, S, p, 0.0, C, p));
+    k_add_diag<<<(unsigned)((p + 127) / 128), 128, 0, ctx->stream>>>(p, C, p, (double)(N - 1));
+    HM_CHECK(chol_factor(ctx, (int)p, C));
+    // D <- D C^-1
+    HM_CHECK(chol_solve_right(ctx, (int)p, C, (int)N, D));
+    // G = S^T E ; E += (D C^-1) G
+    HM_CHECK(hm::dgemm(ctx, true, false, p, M, N, 1.0, S, p, E, ldE, 0.0, G, M));
+    HM_CHECK(hm::dgemm(ctx, false, false, N, M, p, 1.0, D, p, G, M, 1.0, E, ldE));
+    return HM_OK;
+}
+
+extern "C" int hm_es_update_host(hm_ctx* ctx, int64_t N, int64_t M, int64_t p, double* E,
+                                 const double* Eo, const double* obs, const double* perturbs,
+                                 const double* decorr) {
+    HM_REQUIRE(ctx && E && Eo && obs && perturbs && decorr, "null pointer");
+    HM_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    double *dE, *dEo, *dobs, *dpert, *ddec;
+    HM_CHECK(ctx->ws.get("h.E", (size_t)N * M, &dE));
+    HM_CHECK(ctx->ws.get("h.Eo", (size_t)N * p, &dEo));
+    HM_CHECK(ctx->ws.get("h.obsv", (size_t)p, &dobs));
+    HM_CHECK(ctx->ws.get("h.pert", (size_t)N * p, &dpert));
+    HM_CHECK(ctx->ws.get("h.decorr", (size_t)p * p, &ddec));
+    HM_CUDA(cudaMemcpyAsync(dE, E, (size_t)N * M * 8, cudaMemcpyHostToDevice, st));
+    HM_CUDA(cudaMemcpyAsync(dEo, Eo, (size_t)N * p * 8, cudaMemcpyHostToDevice, st));
+    HM_CUDA(cudaMemcpyAsync(dobs, obs, (size_t)p * 8, cudaMemcpyHostToDevice, st));
+    HM_CUDA(cudaMemcpyAsync(dpert, perturbs, (size_t)N * p * 8, cudaMemcpyHostToDevice, st));
+    HM_CUDA(cudaMemcpyAsync(ddec, decorr, (size_t)p * p * 8, cudaMemcpyHostToDevice, st));
+    HM_CHECK(hm_es_update(ctx, N, M, p, dE, M, dEo, dobs, dpert, ddec));
+    HM_CUDA(cudaMemcpyAsync(E, dE, (size_t)N * M * 8, cudaMemcpyDeviceToHost, st));
+    HM_CUDA(cudaStreamSynchronize(st));
+    return HM_OK;
+}
+
+extern "C" int hm_les_update(hm_ctx* ctx, int64_t N, int64_t M, int64_t p, double* E, int64_t ldE,
+                             const double* Eo, const double* obs, const double* perturbs,
+                             const double* decorr, const double* taper) {
+    HM_REQUIRE(ctx && E && Eo && obs && perturbs && decorr && taper, "null pointer");
+    HM_REQUIRE(N > 1 && M > 0 && p > 0 && ldE >= M, "shape");
+    HM_CUDA(cudaSetDevice(ctx->device));
+    const size_t smem = ((size_t)2 * p + (p + 1) / 2 + (size_t)p * p) * sizeof(double);
+    HM_REQUIRE(smem <= 227 * 1024, "p too large for the shared-memory local analysis (p <= 165)");
+    double *S, *D, *A, *B;
+    int* fail;
+    HM_CHECK(whiten(ctx, N, p, Eo, obs, perturbs, decorr, &S, &D));
+    HM_CHECK(ctx->ws.get("an.C", (size_t)p * p, &A));
+    HM_CHECK(ctx->ws.get("an.G", (size_t)p * M, &B));
+    HM_CHECK(ctx->ws.get("an.info", (size_t)4, &fail));
+    HM_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), ctx->stream));
+    HM_CHECK(hm::dgemm(ctx, true, false, p, p, N, 1.0, S, p, S, p, 0.0, A, p));
+    HM_CHECK(hm::dgemm(ctx, true, false, p, M, N, 1.0, S, p, E, ldE, 0.0, B, M));
+    HM_CUDA(cudaFuncSetAttribute(k_local_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_local_analysis<<<(unsigned)M, 256, smem, ctx->stream>>>(M, (int)p, (double)(N - 1), A, taper, B, M, fail);
+    HM_CUDA(cudaGetLastError());
+    HM_CHECK(hm::dgemm(ctx, false, false, N, M, p, 1.0, D, p, B, M, 1.0, E, ldE));
+    return check_info(ctx, fail, "local analysis Cholesky");
+}
+
+extern "C" int hm_ies_step(hm_ctx* ctx, int64_t N, int64_t p, double* W, const double* Eo,
+                           const double* obs, const double* perturbs, const double* decorr,
+                           double xStep) {
+    HM_REQUIRE(ctx && W && Eo && obs && perturbs && decorr, "null pointer");
+    HM_REQUIRE(N > 1 && p > 0, "shape");
+    HM_CUDA(cudaSetDevice(ctx->device));
+    HM_CHECK(ensure_solver(ctx));
+    cudaStream_t st = ctx->stream;
+    double *y, *Dp, *Eow, *LU, *Winv, *mean, *Y0, *res, *G, *Cw, *work;
+    int *ipiv, *info;
+    HM_CHECK(ctx->ws.get("ies.y", (size_t)p, &y));
+    HM_CHECK(ctx->ws.get("ies.Dp", (size_t)N * p, &Dp));
+    HM_CHECK(ctx->ws.get("ies.Eow", (size_t)N * p, &Eow));
+    HM_CHECK(ctx->ws.get("ies.LU", (size_t)N * N, &LU));
+    HM_CHECK(ctx->ws.get("ies.Winv", (size_t)N * N, &Winv));
+    HM_CHECK(ctx->ws.get("ies.mean", (size_t)N, &mean));
+    HM_CHECK(ctx->ws.get("ies.Y0", (size_t)N * p, &Y0));
+    HM_CHECK(ctx->ws.get("ies.res", (size_t)N * p, &res));
+    HM_CHECK(ctx->ws.get("ies.G", (size_t)N * N, &G));
+    HM_CHECK(ctx->ws.get("ies.Cw", (size_t)N * N, &Cw));
+    HM_CHECK(ctx->ws.get("ies.ipiv", (size_t)N, &ipiv));
+    HM_CHECK(ctx->ws.get("an.info", (size_t)4, &info));
+    // y = obs decorr ; Dp = perturbs decorr ; Eo_w = Eo decorr   (HistoryMatch.py:911-912, 927)
+    HM_CHECK(hm::dgemm(ctx, false, false, 1, p, p, 1.0, obs, p, decorr, p, 0.0, y, p));
+    HM_CHECK(hm::dgemm(ctx, false, false, N, p, p, 1.0, perturbs, p, decorr, p, 0.0, Dp, p));
+    HM_CHECK(hm::dgemm(ctx, false, false, N, p, p, 1.0, Eo, p, decorr, p, 0.0, Eow, p));
+    // W^-1 by LU (pinv(W) of the reference; W is square and non-singular).  Row-major W is
+    // column-major W^T and inv(W^T) read back row-major is inv(W).
+    HM_CUDA(cudaMemcpyAsync(LU, W, (size_t)N * N * 8, cudaMemcpyDeviceToDevice, st));
+    int lwork = 0;
+    HM_CUSOLVER(cusolverDnDgetrf_bufferSize(ctx->solver, (int)N, (int)N, LU, (int)N, &lwork));
+    HM_CHECK(ctx->ws.get("ies.getrf_work", (size_t)std::max(lwork, 1), &work));
+    HM_CUSOLVER(cusolverDnDgetrf(ctx->solver, (int)N, (int)N, LU, (int)N, work, ipiv, info));
+    HM_CHECK(check_info(ctx, info, "LU factorisation of W (getrf)"));
+    k_set_identity<<<(unsigned)((N * N + 255) / 256), 256, 0, st>>>(N, Winv);
+    HM_CUSOLVER(cusolverDnDgetrs(ctx->solver, CUBLAS_OP_N, (int)N, (int)N, LU, (int)N, ipiv, Winv, (int)N, info));
+    HM_CHECK(check_info(ctx, info, "LU solve (getrs)"));
+    // Y0 = center(W^-1) Eo_w   (HistoryMatch.py:928)
+    HM_CHECK(hm_center(ctx, N, N, Winv, N, Winv, N, mean, 0));
+    HM_CHECK(hm::dgemm(ctx, false, false, N, p, N, 1.0, Winv, N, Eow, p, 0.0, Y0, p));
+    // grad = (y - Dp - Eo_w) Y0^T + (N-1)(I - W)   (HistoryMatch.py:931-932)
+    k_ies_resid<<<(unsigned)((N * p + 255) / 256), 256, 0, st>>>(N, p, y, Dp, Eow, res);
+    HM_CHECK(hm::dgemm(ctx, false, true, N, N, p, 1.0, res, p, Y0, p, 0.0, G, N));
+    k_ies_grad_b<<<(unsigned)((N * N + 255) / 256), 256, 0, st>>>(N, G, W, (double)(N - 1));
+    // covw = (Y0 Y0^T + (N-1) I)^-1   (HistoryMatch.py:935-938, via the SVD there)
+    HM_CHECK(hm::dgemm(ctx, false, true, N, N, p, 1.0, Y0, p, Y0, p, 0.0, Cw, N));
+    k_add_diag<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(N, Cw, N, (double)(N - 1));
+    HM_CHECK(chol_factor(ctx, (int)N, Cw));
+    // dW = grad covw ; W += xStep dW   (HistoryMatch.py:941-942)
+    HM_CHECK(chol_solve_right(ctx, (int)N, Cw, (int)N, G));
+    k_axpy<<<(unsigned)((N * N + 255) / 256), 256, 0, st>>>(N * N, xStep, G, W);
+    HM_CUDA(cudaGetLastError());
+    return HM_OK;
+}

@@ -1,0 +1,176 @@
+/* hm_b200.h - C ABI of the B200-native history-matching hot path.
+ *
+ * The reference (patnr/HistoryMatching) is pure Python and has no FFI; its
+ * boundary for this path is three Python seams.  Each entry
+ * point below states the reference interface it replaces.  The Python host
+ * side (historymatching_b200/) binds these with ctypes; INTEGRATION.md shows
+ * the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - all floating point data is FP64 (the reference is numpy float64 throughout);
+ *  - "device" pointers are caller-owned CUDA device memory on the ctx's device;
+ *    the library owns only the workspace inside the ctx;
+ *  - work is enqueued on the ctx stream (hm_set_stream); calls that return
+ *    per-member results synchronise that stream before returning where stated;
+ *  - ensemble axis first: a matrix "(N,M)" is row-major with members as rows
+ *    ("transposed" convention, HistoryMatch.py:574-575);
+ *  - flat cell index c = ix*Ny + iy (C-order ravel of an (Nx,Ny) field,
+ *    HistoryMatch.py:163);
+ *  - every function returns 0 on success, a negative hm_status otherwise;
+ *    hm_last_error() gives the message.  One ctx per host thread / GPU.
+ */
+#ifndef HM_B200_H
+#define HM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hm_ctx hm_ctx;
+
+enum hm_status {
+    HM_OK = 0,
+    HM_ERR_CUDA = -1,     /* a CUDA / cuSOLVER call failed */
+    HM_ERR_ARG = -2,      /* invalid argument */
+    HM_ERR_NUMERIC = -3,  /* factorisation failed / non-finite result */
+    HM_ERR_NO_DEVICE = -4
+};
+
+/* per-member status bits written by hm_sim_batch */
+#define HM_MEMBER_CG_NOT_CONVERGED 1
+#define HM_MEMBER_NON_FINITE 2
+
+int hm_version(void);
+const char* hm_last_error(void);
+
+int hm_ctx_create(int device, hm_ctx** out);
+int hm_ctx_destroy(hm_ctx* ctx);
+/* cudaStream_t passed as void*; NULL = the legacy default stream */
+int hm_set_stream(hm_ctx* ctx, void* cuda_stream);
+int hm_synchronize(hm_ctx* ctx);
+
+/* ---------------------------------------------------------------------------
+ * Ensemble forward run.  Replaces, for a whole ensemble at once, the
+ * multiprocessing map  utils.apply(comp1, ...)  (tools/utils.py:155-242,
+ * HistoryMatch.py:358-387) over  ResSim.sim(dt, nSteps, S0)  of the external
+ * TPFA_ResSim package (HistoryMatch.py:224,362; Optimise.py:116): per time
+ * step a TPFA pressure solve, CFL sub-stepped explicit upwind saturation
+ * transport and the gather of saturations at the observation cells
+ * (obs_model, HistoryMatch.py:212-213).
+ * ------------------------------------------------------------------------- */
+typedef struct hm_sim_desc {
+    int32_t n_members;
+    int32_t Nx, Ny;
+    double Lx, Ly;
+    double vw, vo, swc, sor; /* fluid: viscosities, irreducible saturations */
+
+    const double* K;         /* permeability, [member][comp][M] */
+    int64_t K_member_stride; /* elements; 0 = one field shared by all members */
+    int64_t K_comp_stride;   /* elements from Kx to Ky; 0 = isotropic */
+    const double* por;       /* [M] porosity or NULL (= 1) */
+
+    int32_t n_wells;
+    const int32_t* well_cell; /* [member][well] flat cell index */
+    int64_t well_cell_member_stride; /* 0 = shared */
+    const double* well_rate;  /* signed: + injection, - production; [member][step][well] */
+    int64_t well_rate_member_stride; /* 0 = shared */
+    int64_t well_rate_step_stride;   /* 0 = constant in time */
+
+    const double* S0;         /* initial water saturation [member][M] */
+    int64_t S0_member_stride; /* 0 = shared */
+    double dt;
+    int32_t n_steps;
+
+    int32_t n_obs;
+    const int32_t* obs_cell;  /* [n_obs] cells whose saturation is observed */
+
+    double* S_last;   /* out [member][M] saturation after the last step */
+    double* S_hist;   /* out NULL or [member][n_steps+1][M], row 0 = S0 */
+    double* obs;      /* out NULL or [member][n_steps][n_obs] */
+    double* P_last;   /* out NULL or [member][M] pressure of the last step */
+    int32_t* status;  /* out NULL or [member] HM_MEMBER_* bits */
+    int32_t* substeps; /* out NULL or [member][n_steps] CFL sub-step counts */
+    int32_t* cg_iters; /* out NULL or [member][n_steps] pressure-solver iterations */
+
+    double cg_rtol;      /* <=0: default 1e-12 (||r|| <= rtol ||q||) */
+    int32_t cg_max_iter; /* <=0: default 100*(Nx+Ny)+200 */
+    int32_t chunk_members; /* <=0: all members in one launch wave */
+    int32_t reserved;
+} hm_sim_desc;
+
+/* statistics of the last hm_sim_batch on this ctx (host side) */
+typedef struct hm_sim_stats {
+    int64_t cg_iterations;   /* sum over steps of the iterations launched */
+    int64_t sat_substeps;    /* sum over steps of max-over-members sub-steps */
+    int64_t kernel_launches; /* kernels launched by the call */
+    int64_t cg_kernel_launches;
+    int64_t sat_kernel_launches;
+} hm_sim_stats;
+
+/* All pointers in the descriptor are DEVICE pointers.  Synchronises the ctx
+ * stream before returning (the sub-step count is data dependent). */
+int hm_sim_batch(hm_ctx* ctx, const hm_sim_desc* desc);
+/* Same with HOST pointers: stages through device memory owned by the ctx
+ * (host->device and device->host copies happen inside the call). */
+int hm_sim_batch_host(hm_ctx* ctx, const hm_sim_desc* desc);
+int hm_sim_get_stats(hm_ctx* ctx, hm_sim_stats* out);
+/* ms of device time per phase of the last hm_sim_batch: [setup, cg, flux, saturation, obs] */
+int hm_sim_get_phase_ms(hm_ctx* ctx, double out[5]);
+
+/* ---------------------------------------------------------------------------
+ * Dense FP64 building block (tensor-core DMMA).  C = alpha*op(A)*op(B) + beta*C,
+ * row-major, op = transpose when the flag is non-zero.  Replaces the numpy
+ * "@" products of HistoryMatch.py:583-586, 920, 928-941.
+ * ------------------------------------------------------------------------- */
+int hm_dgemm(hm_ctx* ctx, int transA, int transB, int64_t m, int64_t n, int64_t k,
+             double alpha, const double* A, int64_t lda, const double* B, int64_t ldb,
+             double beta, double* C, int64_t ldc);
+
+/* ---------------------------------------------------------------------------
+ * ES analysis.  Replaces ens_update0 (HistoryMatch.py:578-586):
+ *   E + D pinv(S^T S + (N-1) I) S^T X,  S = center(Eo) decorr,
+ *   D = (obs - Eo - perturbs) decorr,  X = center(E).
+ * E (N,M) is updated in place for the column range [col0, col0+ncols) it
+ * holds (parameter-sharded multi-GPU use passes its own column block; Eo,
+ * perturbs are always the full (N,p) blocks).  ldE = row stride of E.
+ * ------------------------------------------------------------------------- */
+int hm_es_update(hm_ctx* ctx, int64_t N, int64_t M, int64_t p, double* E, int64_t ldE,
+                 const double* Eo, const double* obs, const double* perturbs,
+                 const double* decorr);
+int hm_es_update_host(hm_ctx* ctx, int64_t N, int64_t M, int64_t p, double* E,
+                      const double* Eo, const double* obs, const double* perturbs,
+                      const double* decorr);
+
+/* Localised ES.  Replaces ens_update0_loc (HistoryMatch.py:774-797):
+ * one tapered local analysis per parameter (column of E).  taper is (M,p)
+ * row-major for the M columns held; entries with sqrt(taper) <= 1e-2 are
+ * excluded exactly as in the reference. */
+int hm_les_update(hm_ctx* ctx, int64_t N, int64_t M, int64_t p, double* E, int64_t ldE,
+                  const double* Eo, const double* obs, const double* perturbs,
+                  const double* decorr, const double* taper);
+
+/* Distance taper computed on the device.  Replaces
+ * loc.bump(loc.pairwise_distances(xy_prm, xy_obs) / radius, sharpness)
+ * (tools/localization.py:9-92; HistoryMatch.py:717,863): out is (M,p). */
+int hm_taper_bump(hm_ctx* ctx, int64_t M, int64_t p, const double* xy_prm /* (M,2) */,
+                  const double* xy_obs /* (p,2) */, double radius, double sharpness,
+                  double* out);
+
+/* Anomalies and mean.  Replaces utils.center (tools/utils.py:10-28) along axis 0:
+ * X = E - mean (may alias E), mean (M,) may be NULL; scale = sqrt(N/(N-1)) if rescale. */
+int hm_center(hm_ctx* ctx, int64_t N, int64_t M, const double* E, int64_t ldE, double* X,
+              int64_t ldX, double* mean, int rescale);
+
+/* One Gauss-Newton step of the iterative smoother in the ensemble subspace.
+ * Replaces the loop body of IES (HistoryMatch.py:927-942): given W (N,N), the
+ * predicted data Eo (N,p) of E = x0 + W X0, y = obs decorr, Dp = perturbs decorr
+ * it overwrites W with W + xStep * (grad_y + grad_b) covw. */
+int hm_ies_step(hm_ctx* ctx, int64_t N, int64_t p, double* W, const double* Eo,
+                const double* obs, const double* perturbs, const double* decorr, double xStep);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HM_B200_H */

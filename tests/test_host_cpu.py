@@ -1,0 +1,248 @@
+"""CPU tests (-m "not gpu"): host-side logic of the drop-ins, the C-ABI surface,
+and the golden vectors through the drop-in numpy helpers.  No GPU compute."""
+
+import copy
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+import historymatching_b200 as hmb
+
+hmb.activate()
+import tools.localization as loc  # noqa: E402
+import TPFA_ResSim as simulator  # noqa: E402
+from tools import geostat, utils  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from historymatching_b200 import _lib
+
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "hm_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(hm_\w+)\s*\(", header, flags=re.M))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.hm_version() >= 100
+    # struct mirrors match the header's field order
+    fields = re.search(r"typedef struct hm_sim_desc \{(.*?)\} hm_sim_desc;", header, flags=re.S).group(1)
+    fields = re.sub(r"/\*.*?\*/", "", fields, flags=re.S)
+    names = []
+    for decl in fields.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names += [n.strip().lstrip("*") for n in decl.split()[-1:]] if "," not in decl else [
+            n.strip().lstrip("*") for n in re.sub(r"^\s*(const\s+)?\w+\s*\**", "", decl).split(",")]
+    assert names == [f[0] for f in _lib.SimDesc._fields_]
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from historymatching_b200 import _lib
+    from historymatching_b200 import analysis as ha
+
+    with pytest.raises(_lib.HmError):
+        _lib.Context(0)
+    with pytest.raises(_lib.HmError):
+        ha.ens_update0(np.zeros((3, 4)), np.zeros((3, 2)), np.zeros(2), np.zeros((3, 2)), np.eye(2))
+    m = simulator.ResSim(Nx=4, Ny=4)
+    m.inj_xy, m.prd_xy, m.inj_rates, m.prd_rates = [[0.1, 0.1]], [[0.9, 0.9]], [[1]], [[1]]
+    with pytest.raises(_lib.HmError):
+        m.sim(0.1, 1, np.zeros(16))
+
+
+def test_utils_primitives_golden(golden):
+    g = golden("primitives.npz")
+    X, x = utils.center(g["E"])
+    np.testing.assert_array_equal(X, g["center_X"])
+    np.testing.assert_array_equal(x, g["center_x"])
+    np.testing.assert_array_equal(utils.center(g["E"], rescale=True)[0], g["center_X_rescaled"])
+    np.testing.assert_array_equal(utils.cov(g["E"], g["b"]), g["cov"])
+    np.testing.assert_array_equal(utils.corr(g["E"], g["b"][:, 0]), g["corr"])
+    np.testing.assert_allclose(utils.rinv(g["A"], 0.1), g["rinv_tikh"], rtol=1e-12)
+    np.testing.assert_allclose(utils.rinv(g["A"], 0.1, tikh=False), g["rinv_trunc"], rtol=1e-12)
+    np.testing.assert_array_equal(loc.pairwise_distances(g["pts_a"], g["pts_b"]), g["pd_ab"])
+    np.testing.assert_array_equal(loc.pairwise_distances(g["pts_a"], g["pts_b"], domain=(2, 1)), g["pd_periodic"])
+    np.testing.assert_array_equal(loc.bump(g["dist"]), g["bump1"])
+    np.testing.assert_array_equal(loc.bump(g["dist"], 10), g["bump_sharp"])
+    np.testing.assert_array_equal(geostat.variogram_gauss(np.array([0.0, 1.0, 2.0]), 1, n=0.1, a=1), g["variogram"])
+
+
+def test_localization_doctests():
+    A = np.arange(4)[:, None]
+    np.testing.assert_array_equal(loc.pairwise_distances(A, [[2]]).T, [[2.0, 1.0, 0.0, 1.0]])
+    np.testing.assert_array_equal(loc.pairwise_distances(A, domain=(4,))[1], [1.0, 0.0, 1.0, 2.0])
+    np.testing.assert_array_equal(loc.pairwise_distances(np.arange(4)), [[0.0]])
+    batches = loc.rectangular_partitioning([4, 13], [2, 4])
+    assert sorted(np.concatenate(batches)) == list(range(52))
+
+
+def test_prior_bit_exact_and_stream_order(golden):
+    """seed(1) -> truth -> prior, HistoryMatch.py:78,167,290: identical draws, no extra numbers."""
+    g = golden("prior_20x20_seed1.npz")
+    model = simulator.ResSim(Nx=20, Ny=20, Lx=2, Ly=1)
+    np.random.seed(1)
+    truth = geostat.gaussian_fields(model.mesh, 1, r=0.8)
+    prior = geostat.gaussian_fields(model.mesh, 40, r=0.8)
+    nxt = np.random.randn()
+    np.testing.assert_array_equal(truth, g["truth"])
+    np.testing.assert_array_equal(prior, g["prior"])
+    np.random.seed(1)
+    np.random.randn(41, 400)
+    assert nxt == np.random.randn()
+
+
+def test_separable_prior_statistics():
+    model = simulator.ResSim(Nx=24, Ny=16, Lx=2, Ly=1)
+    F = geostat.gaussian_fields_separable(model, N=3000, r=0.8, rng=np.random.RandomState(0))
+    assert F.shape == (3000, 24 * 16)
+    C = np.cov(F.T)
+    X = geostat.vectorize(*model.mesh)
+    want = 1 - geostat.variogram_gauss(geostat.dist_euclid(X), 0.8)
+    assert np.abs(C - want).max() < 0.12
+    assert abs(F.var() - 1) < 0.05
+
+
+def test_ressim_surface_and_validation():
+    model = simulator.ResSim(Nx=20, Ny=20, Lx=2, Ly=1, name="Base")
+    assert model.shape == (20, 20) and model.Nxy == 400 and model.domain[1] == (2, 1)
+    assert model.mesh[0].shape == (20, 20) and model.name == "Base"
+    # K setter forms used by the notebooks: (2,Nx,Ny), (1,Nxy), (Nxy,)
+    p = np.random.RandomState(0).rand(20, 20) + 0.5
+    for val in (np.stack([p, p]), p.reshape(1, -1), p.ravel()):
+        model.K = val
+        assert model.K.shape == (2, 20, 20)
+        np.testing.assert_array_equal(model.K[0], p)
+    with pytest.raises(ValueError):
+        model.K = -p
+    # wells: list of [x, y], flat arrays; collocated with cell centres
+    near01 = np.array([0.12, 0.87])
+    model.prd_xy = [[x, y] for y in model.Ly * near01 for x in model.Lx * near01]
+    model.inj_xy = np.array([1.0, 0.5])
+    assert model.prd_xy.shape == (4, 2) and model.inj_xy.shape == (1, 2) and model.nPrd == 4 and model.nInj == 1
+    np.testing.assert_allclose(model.inj_xy, [[1.05, 0.525]])
+    x, y = model.prd_xy.T
+    np.testing.assert_array_equal(model.xy2ind(x, y), model.xy2ind(*model.ind2xy(model.xy2ind(x, y))))
+    assert model.ind2xy(np.arange(400)).shape == (2, 400) and model.ind2xy(7).shape == (2,)
+    assert model.sub2ind(3, 4) == 64 and tuple(model.sub2xy(0, 0)) == (0.05, 0.025)
+    with pytest.raises(ValueError):
+        model.inj_xy = [[2.5, 0.5]]
+    with pytest.raises(ValueError):
+        model.inj_xy = [[np.nan, 0.5]]
+    model.inj_rates = [[1]]
+    model.prd_rates = np.ones((4, 1)) / 4
+    rates, cells = model._schedule(5)
+    assert rates.shape == (5, 5) and cells.dtype == np.int32 and np.allclose(rates.sum(1), 0)
+    assert model.actual_rates["inj"].shape == (1, 5) and model.actual_rates["prd"].shape == (4, 5)
+    model.prd_rates = np.ones(4)  # 1-D form (Optimise.py:643-645)
+    assert model.prd_rates.shape == (4, 1)
+    with pytest.raises(ValueError):  # unbalanced: raises at run (HistoryMatch.py:182-184)
+        model._schedule(5)
+    m2 = copy.deepcopy(model)
+    m2.K = 2 * model.K
+    assert not np.array_equal(m2.K, model.K)
+    import dill
+
+    assert dill.loads(dill.dumps(model)).Nxy == 400
+
+
+def test_apply_contract_serial_and_threaded():
+    calls = []
+
+    def f(a, b, c=0):
+        calls.append(a)
+        return a + b.sum() + c
+
+    A, B, Cc = np.arange(5), np.ones((5, 3)), np.arange(5) * 10
+    for n in (1, False, "auto", 4, True, None):
+        utils.nCPU = n
+        out = utils.apply(f, A, B, c=Cc, pbar=False)
+        assert out == [a + 3 + 10 * a for a in range(5)]
+    with pytest.raises(ValueError):
+        utils.apply(f, A, B[:4], pbar=False)
+    utils.nCPU = "auto"
+
+    def boom(a):
+        if a == 2:
+            raise KeyError("member 2")
+        return a
+
+    with pytest.raises(KeyError):
+        utils.apply(boom, A, pbar=False)
+    # pbar forms: str, dict, existing tqdm (re-used, not closed)
+    bar = utils.progbar(total=3, disable=True)
+    for pb in ("desc", dict(desc="x", leave=False, disable=True), bar):
+        assert utils.apply(lambda a: a, A, pbar=pb) == list(A)
+    utils.nCPU = 1
+
+
+def test_collector_batches_sim_calls(monkeypatch):
+    """apply() gathers the members' ResSim.sim calls into ONE batched request list."""
+    batches = []
+
+    def fake_run(reqs):
+        batches.append(len(reqs))
+        for r in reqs:
+            if r.S0[0] < 0:
+                r.error = RuntimeError("bad member")
+            else:
+                r.result = np.tile(r.S0, (r.nSteps + 1, 1)) + r.K[0].mean()
+            r.done = True
+
+    monkeypatch.setattr(simulator, "run_requests", fake_run)
+    model = simulator.ResSim(Nx=4, Ny=4, Lx=1, Ly=1)
+    model.inj_xy, model.prd_xy, model.inj_rates, model.prd_rates = [[0.1, 0.1]], [[0.9, 0.9]], [[1]], [[1]]
+
+    def comp(k, s0):
+        m = copy.deepcopy(model)
+        m.K = np.full(16, k)
+        try:
+            w = m.sim(0.1, 2, s0, pbar=False)
+        except RuntimeError:
+            return -1.0
+        return w[-1, 0]
+
+    ks = np.arange(1.0, 9.0)
+    s0 = np.zeros((8, 16))
+    s0[3] = -1
+    utils.nCPU = "auto"
+    out = utils.apply(comp, ks, s0, pbar=False)
+    assert batches == [8]
+    assert out == [1.0, 2.0, 3.0, -1.0, 5.0, 6.0, 7.0, 8.0]
+    # members that never reach sim() (invalid parameters raise first, Optimise.py:548-555)
+    def comp2(k):
+        m = copy.deepcopy(model)
+        try:
+            if k > 6:
+                m.inj_xy = [[5.0, 5.0]]
+            return m.sim(0.1, 1, np.zeros(16), pbar=False)[-1, 0] + k
+        except ValueError:
+            return 0.0
+
+    batches.clear()
+    out = utils.apply(comp2, ks, pbar=False)
+    assert batches == [6] and out[-2:] == [0.0, 0.0] and out[0] == 2.0
+    utils.nCPU = 1
+    batches.clear()
+    utils.apply(comp2, ks[:3], pbar=False)
+    assert batches == [1, 1, 1]
+
+
+def test_enopt_on_quadratic():
+    from tools import enopt
+
+    utils.nCPU = 1
+    np.random.seed(3)
+    obj = lambda u: -np.sum((u - np.array([1.0, -2.0])) ** 2)  # noqa: E731
+    path, objs, info = enopt.GD(obj, np.zeros(2), enopt.nabla_ens(0.1, nEns=12), quiet=True)
+    assert np.linalg.norm(path[-1] - [1, -2]) < 0.05 and objs[-1] > objs[0]

@@ -1,0 +1,174 @@
+"""GPU parity: hm_sim_batch (CUDA, through the C ABI) vs the CPU oracle.
+
+Tolerances (north_star: "within a stated relative tolerance, e.g. 1e-8 FP64"):
+pressures 1e-8 of the pressure range, saturations / production curves atol 1e-8
+(saturations are O(1)); CFL sub-step counts must agree exactly.
+
+Double-precision floor: the face flux is (P_a - P_b) * T with P = O(1), so it
+carries an absolute error ~ eps * T_max in BOTH implementations, and the oracle's
+direct solve has a forward error ~ cond(A) * eps.  For permeabilities up to ~1e5
+(|log-perm| <= 2.3 under K = 0.1 + exp(5x)) this stays below 1e-9 and the 1e-8
+tolerance holds; for the rare members of the notebook prior with K up to 3e8
+(x = 3.9) neither implementation is accurate to 1e-8 and the tolerance is
+stated as 4 * eps * K_max * nSteps (test_extreme_contrast_floor).
+"""
+
+import numpy as np
+import pytest
+
+from oracle import ressim as orr
+
+pytestmark = pytest.mark.gpu
+
+SAT_TOL = 1e-8
+
+
+def _setup(Nx, Ny, N, seed, rough=1.0, clip=2.2):
+    from historymatching_b200.sim import GridSpec
+
+    m = orr.notebook_model(Nx, Ny)
+    rng = np.random.RandomState(seed)
+    # smooth-ish random log-permeability with the notebook's contrast (K = 0.1 + exp(5x))
+    x = rng.randn(N, Nx // 4 + 2, Ny // 4 + 2)
+    x = np.kron(x, np.ones((4, 4)))[:, :Nx, :Ny]
+    for _ in range(3):
+        x = 0.25 * (np.roll(x, 1, 1) + np.roll(x, -1, 1) + np.roll(x, 1, 2) + np.roll(x, -1, 2))
+    x = np.clip(rough * x / x.std(), -clip, clip)
+    logk = x.reshape(N, -1)
+    grid = GridSpec(Nx=Nx, Ny=Ny, Lx=m.Lx, Ly=m.Ly)
+    inj = m.xy2ind(*m.inj_xy.T)
+    prd = m.xy2ind(*m.prd_xy.T)
+    cells = np.concatenate([inj, prd]).astype(np.int32)
+    rates = np.concatenate([m.inj_rates[:, 0], -m.prd_rates[:, 0]])
+    return m, grid, logk, cells, rates, prd.astype(np.int32)
+
+
+def _oracle(m, logk, dt, nT, S0, prd):
+    outs = [orr.forward_member(m, lk, dt, nT, S0 if S0.ndim == 1 else S0[i], prd) for i, lk in enumerate(logk)]
+    return np.array([o[0] for o in outs]), np.array([o[1] for o in outs])
+
+
+@pytest.mark.parametrize("Nx,Ny,N,nT", [(20, 20, 6, 40), (33, 17, 3, 5), (64, 64, 2, 3)])
+def test_forward_ensemble_matches_oracle(Nx, Ny, N, nT):
+    from historymatching_b200.sim import run_ensemble
+
+    m, grid, logk, cells, rates, prd = _setup(Nx, Ny, N, seed=Nx + Ny)
+    dt = 0.025
+    S0 = np.zeros(grid.M)
+    res = run_ensemble(grid, orr.perm_transf(logk), cells, rates, S0, dt, nT, obs_cell=prd,
+                       history=True, pressure=True, want_substeps=True)
+    assert not res.status.any()
+    wsats, prods = _oracle(m, logk, dt, nT, S0, prd)
+    np.testing.assert_array_equal(res.S_hist[:, 0], 0.0)
+    np.testing.assert_allclose(res.S_hist, wsats, rtol=0, atol=SAT_TOL)
+    np.testing.assert_allclose(res.obs, prods, rtol=0, atol=SAT_TOL)
+    np.testing.assert_allclose(res.S_last, wsats[:, -1], rtol=0, atol=SAT_TOL)
+    # sub-step counts are integers of the flow field: must match exactly
+    mm = orr.notebook_model(Nx, Ny)
+    p = orr.perm_transf(logk[0]).reshape(mm.shape)
+    mm.K = np.stack([p, p])
+    _, aux = mm.sim(dt, nT, S0, return_aux=True)
+    np.testing.assert_array_equal(res.substeps[0], aux["Nts"])
+    P = aux["P"][-1]
+    np.testing.assert_allclose(res.P_last[0], P, rtol=0, atol=1e-8 * np.abs(P).max())
+
+
+def test_device_path_equals_host_path():
+    import torch
+
+    from historymatching_b200.sim import run_ensemble
+
+    m, grid, logk, cells, rates, prd = _setup(20, 20, 4, seed=3)
+    K = orr.perm_transf(logk)
+    host = run_ensemble(grid, K, cells, rates, np.zeros(grid.M), 0.025, 4, obs_cell=prd)
+    dev = run_ensemble(grid, torch.as_tensor(K, device="cuda"), cells, rates, np.zeros(grid.M), 0.025, 4,
+                       obs_cell=prd)
+    np.testing.assert_array_equal(host.S_last, dev.S_last.cpu().numpy())
+    np.testing.assert_array_equal(host.obs, dev.obs.cpu().numpy())
+    assert dev.stats["kernel_launches"] > 0
+
+
+def test_restart_and_per_member_state():
+    """forward_model(perm, wsat.curnt) (HistoryMatch.py:1227): per-member initial saturation."""
+    from historymatching_b200.sim import run_ensemble
+
+    m, grid, logk, cells, rates, prd = _setup(20, 20, 3, seed=11)
+    K = orr.perm_transf(logk)
+    full = run_ensemble(grid, K, cells, rates, np.zeros(grid.M), 0.025, 8, obs_cell=prd)
+    first = run_ensemble(grid, K, cells, rates, np.zeros(grid.M), 0.025, 4, obs_cell=prd)
+    second = run_ensemble(grid, K, cells, rates, first.S_last, 0.025, 4, obs_cell=prd)
+    np.testing.assert_allclose(second.S_last, full.S_last, rtol=0, atol=1e-9)  # cold vs warm CG start
+    np.testing.assert_allclose(second.obs, full.obs[:, 4:], rtol=0, atol=1e-9)
+
+
+def test_per_member_wells_and_schedules():
+    """EnOpt-style batches (Optimise.py:112-125): wells / rates differ per member."""
+    from historymatching_b200.sim import GridSpec, run_ensemble
+
+    Nx = Ny = 16
+    nT, dt = 6, 0.025
+    grid = GridSpec(Nx=Nx, Ny=Ny, Lx=2.0, Ly=1.0)
+    rng = np.random.RandomState(5)
+    K = np.exp(rng.randn(Nx * Ny) * 0.5)
+    N = 3
+    wc = np.zeros((N, 3), np.int32)
+    wr = np.zeros((N, nT, 3))
+    S_ref = []
+    for i in range(N):
+        m = orr.OracleResSim(Nx, Ny, 2.0, 1.0)
+        m.K = np.stack([K.reshape(Nx, Ny)] * 2)
+        m.inj_xy = m.ind2xy(np.array([rng.randint(Nx * Ny)])).T
+        m.prd_xy = m.ind2xy(rng.choice(Nx * Ny, 2, replace=False)).T
+        inj = 0.5 + rng.rand(1, nT)
+        split = rng.rand(1, nT)
+        m.inj_rates = inj
+        m.prd_rates = np.concatenate([inj * split, inj * (1 - split)])
+        wc[i] = np.concatenate([m.xy2ind(*m.inj_xy.T), m.xy2ind(*m.prd_xy.T)])
+        wr[i] = np.concatenate([m.inj_rates, -m.prd_rates]).T
+        S_ref.append(m.sim(dt, nT, np.zeros(Nx * Ny)))
+    res = run_ensemble(grid, K, wc, wr, np.zeros(Nx * Ny), dt, nT, history=True, n_members=N)
+    assert not res.status.any()
+    np.testing.assert_allclose(res.S_hist, np.array(S_ref), rtol=0, atol=SAT_TOL)
+
+
+def test_full_size_properties():
+    """BASELINE config sizes (128^2): size-independent invariants instead of the oracle."""
+    import torch
+
+    from historymatching_b200.sim import run_ensemble
+
+    m, grid, logk, cells, rates, prd = _setup(128, 128, 8, seed=1)
+    K = torch.as_tensor(orr.perm_transf(logk), device="cuda")
+    nT, dt = 3, 0.025
+    res = run_ensemble(grid, K, cells, rates, torch.zeros(grid.M, dtype=torch.float64, device="cuda"), dt, nT,
+                       obs_cell=prd, history=True, want_substeps=True)
+    S = res.S_hist.cpu().numpy()
+    assert not res.status.cpu().numpy().any()
+    assert (res.substeps.cpu().numpy() == 615).all()
+    assert S.min() >= 0 and S.max() < 1
+    vol = S.sum(-1) * (grid.Lx / grid.Nx) * (grid.Ly / grid.Ny)
+    np.testing.assert_allclose(vol, np.broadcast_to(dt * np.arange(nT + 1), vol.shape), rtol=1e-10, atol=1e-13)
+    assert np.abs(res.obs.cpu().numpy()).max() < 1e-12  # no breakthrough yet
+
+
+def test_extreme_contrast_floor(golden):
+    """The notebook's own seed-1 prior (HistoryMatch.py:78,290) contains K up to 2.8e8."""
+    from historymatching_b200.sim import run_ensemble
+
+    m, grid, _, cells, rates, prd = _setup(20, 20, 1, seed=0)
+    logk = golden("prior_20x20_seed1.npz")["prior"][[2, 6, 36, 0, 1]]
+    nT, dt = 40, 0.025
+    S0 = np.zeros(grid.M)
+    res = run_ensemble(grid, orr.perm_transf(logk), cells, rates, S0, dt, nT, obs_cell=prd, history=True)
+    assert not res.status.any()
+    eps = np.finfo(float).eps
+    for i, lk in enumerate(logk):
+        for refine in (0, 3):
+            mm = orr.notebook_model(20, 20)
+            p = orr.perm_transf(lk).reshape(mm.shape)
+            mm.K = np.stack([p, p])
+            mm.refine = refine
+            ref = mm.sim(dt, nT, S0)
+            tol = max(SAT_TOL, 4 * eps * p.max() * nT)
+            err = np.abs(res.S_hist[i] - ref).max()
+            assert err <= tol, (i, refine, err, tol)
