@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Benchmark of the history-matching hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A *step* is one ES-MDA assimilation pass over the synthetic ensemble: the
+forward run of every member for ``nTime`` = 40 simulator steps (pressure solve +
+CFL sub-stepped transport + observation gather) followed by the ES update
+(``alpha = 4``, one of the ``Na = 4`` passes) of the whole parameter ensemble.
+``value`` = member*steps per second = members * nTime * K / time.
+
+Workload (``config.workload``): BASELINE config "ES-MDA on a 128x128 synthetic
+permeability grid, 1024 members, 1 B200"; with ``--gpus N`` every GPU holds 1024
+members (weak scaling, members sharded, NCCL all-gather of the predicted data and
+all-to-all re-shard of the parameter matrix inside the update).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "A": dict(Nx=20, Ny=20, members=40, nTime=40, name="HistoryMatch.ipynb default: 20x20 grid, 40 members"),
+    "C": dict(Nx=128, Ny=128, members=1024, nTime=40,
+              name="ES-MDA pass, 128x128 synthetic permeability grid, 1024 members per GPU"),
+    "D": dict(Nx=512, Ny=512, members=512, nTime=40,
+              name="ES-MDA pass, 512x512 grid, 512 members per GPU (4096 on 8 GPUs)"),
+}
+ALPHA = 4.0
+PEAKS_FALLBACK = dict(hbm_gbs=6650.0)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C", choices=list(WORKLOADS))
+    ap.add_argument("--members", type=int, default=0, help="override members per GPU (development)")
+    ap.add_argument("--ntime", type=int, default=0, help="override simulator steps per pass (development)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the baseline sample")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path)), "measured"
+    return PEAKS_FALLBACK, "fallback"
+
+
+# ---- clocks ----------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples if len(s) >= 6 for n, v in zip(names, s[2:6]) if v == "Active"})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+# ---- CPU reference path (oracle port of the reference's scipy/numpy path) ---------------------
+def _cpu_member(args):
+    import threadpoolctl
+
+    threadpoolctl.threadpool_limits(1)  # the reference pins BLAS to 1 thread per worker (tools/utils.py:207-209)
+    from oracle import ressim as orr
+
+    Nx, Ny, logk, dt, nT = args
+    m = orr.notebook_model(Nx, Ny)
+    prd = m.xy2ind(*m.prd_xy.T)
+    return orr.forward_member(m, logk, dt, nT, np.zeros(m.Nxy), prd)[1]
+
+
+def cpu_forward_sample(wl, seconds, seed=0):
+    """Time the oracle forward run on the host cores on a bounded sample; member*steps/s."""
+    import multiprocessing as mp
+
+    from historymatching_b200.dropin.tools import geostat
+    from historymatching_b200.sim import GridSpec
+
+    cores = min(mp.cpu_count(), 64)
+    grid = GridSpec(wl["Nx"], wl["Ny"], 2.0, 1.0)
+    # cost model from SURVEY.md section 6: ~0.215 s per member-step per core at 128^2 (x (cells/16384)^1.7)
+    per = 0.215 * (grid.M / 16384.0) ** 1.7 if grid.M > 1000 else 0.0016
+    nT = int(max(1, min(wl["nTime"], seconds / per)))
+    members = cores if per * nT * 1.0 < seconds else max(1, int(cores * seconds / (per * nT)))
+    members = max(1, min(members, cores * max(1, int(seconds / (per * nT)))))
+    logk = geostat.gaussian_fields_separable(grid, members, r=0.8, rng=np.random.RandomState(seed))
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_cpu_member, [(grid.Nx, grid.Ny, logk[0], 0.025, 1)] * cores)  # warm the workers
+        t0 = time.perf_counter()
+        pool.map(_cpu_member, [(grid.Nx, grid.Ny, lk, 0.025, nT) for lk in logk], chunksize=1)
+        dt = time.perf_counter() - t0
+    return members * nT / dt, cores, f"{members} members x {nT} steps of the {grid.Nx}x{grid.Ny} forward run, oracle (scipy spsolve + explicit upwind), one process per core, BLAS pinned to 1 thread"
+
+
+def run_reference(args, wl, rank):
+    if rank != 0:
+        return
+    vals = []
+    sample = ""
+    cores = 0
+    per_step = max(5.0, min(args.cpu_seconds, 240.0 / max(1, args.steps + args.warmup)))
+    for i in range(args.warmup + args.steps):
+        v, cores, sample = cpu_forward_sample(wl, per_step, seed=i)
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    line = dict(metric="ensemble forward-sim member*steps/s", value=value, unit="member*steps/s", impl="reference",
+                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * wl["members"] * wl["nTime"] / value, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=wl["name"], grid=[wl["Nx"], wl["Ny"]], members_per_gpu=wl["members"],
+                            nTime=wl["nTime"]),
+                cpu_baseline=dict(value=value, unit="member*steps/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=value, unit="member*steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# ---- GPU arm ------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    wl = dict(WORKLOADS[args.workload])
+    if args.members:
+        wl["members"] = args.members
+    if args.ntime:
+        wl["nTime"] = args.ntime
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, wl, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from historymatching_b200 import _lib
+    from historymatching_b200 import analysis as ha
+    from historymatching_b200 import dist as hd
+    from historymatching_b200.dropin.tools import geostat
+    from historymatching_b200.workflow import HistoryMatchCase
+
+    case = HistoryMatchCase(wl["Nx"], wl["Ny"], 2.0, 1.0, 0.025, wl["nTime"])
+    M, p = case.grid.M, case.p
+    N_loc = wl["members"]
+    N = N_loc * world
+    lo, hi = hd.member_slice(N, rank, world)
+
+    # synthetic inputs: separable Gaussian-variogram prior (r = 0.8), truth drawn first (seed 1)
+    truth = geostat.gaussian_fields_separable(case.grid, 1, r=0.8, rng=np.random.RandomState(1), device=dev)
+    E0 = geostat.gaussian_fields_separable(case.grid, N_loc, r=0.8, rng=np.random.RandomState(100 + rank), device=dev)
+    obs_truth, _ = case.forward(truth)
+    g = torch.Generator(device=dev).manual_seed(7)
+    R12T = torch.as_tensor(case.R12.T.copy(), device=dev)
+    noisy = (obs_truth[0] + torch.randn(p, dtype=torch.float64, device=dev, generator=g) @ R12T).clamp(0, 1)
+    Z = torch.randn(N, p, dtype=torch.float64, device=dev, generator=g)  # same stream on every rank
+    pert = np.sqrt(ALPHA) * (Z @ R12T)
+    dec = torch.as_tensor(case.decorr / np.sqrt(ALPHA), device=dev)
+    ctx = _lib.Context.get(local_rank)
+
+    last = {}
+
+    def one_pass(E):
+        Eo, res = case.forward(E, want_substeps=True)
+        last["res"] = res
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        post = hd.sharded_update(ha.ens_update0, E, Eo, N, obs=noisy, perturbs=pert, decorr=dec)
+        t1.record()
+        last["upd"] = (t0, t1)
+        return post, Eo
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_pass(E0)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    l0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    phase = dict(setup=0.0, cg=0.0, flux=0.0, saturation=0.0, obs=0.0)
+    upd_ms, cg_member_iters, sat_member_substeps = 0.0, 0, 0
+    stats_acc = dict(cg_kernel_launches=0, sat_kernel_launches=0)
+    for _ in range(args.steps):
+        post, Eo = one_pass(E0)
+        torch.cuda.synchronize()
+        res = last["res"]
+        for k in phase:
+            phase[k] += res.stats["phase_ms"][k]
+        upd_ms += last["upd"][0].elapsed_time(last["upd"][1])
+        cg_member_iters += int(res.cg_iters.sum())
+        sat_member_substeps += int(res.substeps.sum())
+        for k in stats_acc:
+            stats_acc[k] += res.stats[k]
+    ev1.record()
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    launches = ctx.launch_count() - l0
+    value = N * wl["nTime"] * args.steps / (ms / 1e3)
+    bad = int((last["res"].status != 0).sum())
+
+    # ---- end to end through the host-buffer API -------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        x_host = E0.cpu().pin_memory()
+        pert_host, noisy_host = pert.cpu().pin_memory(), noisy.cpu().pin_memory()
+        out_host = torch.empty_like(x_host).pin_memory()
+        eo_host = torch.empty((N_loc, p), dtype=torch.float64).pin_memory()
+
+        def e2e_pass():
+            E = x_host.to(dev, non_blocking=True)
+            pr = pert_host.to(dev, non_blocking=True)
+            ob = noisy_host.to(dev, non_blocking=True)
+            Eo, _ = case.forward(E)
+            post = hd.sharded_update(ha.ens_update0, E, Eo, N, obs=ob, perturbs=pr, decorr=dec)
+            out_host.copy_(post, non_blocking=True)
+            eo_host.copy_(Eo, non_blocking=True)
+
+        e2e_pass()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, 2))
+        for _ in range(n_e2e):
+            e2e_pass()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = dict(value=N * wl["nTime"] * n_e2e / float(dt), unit="member*steps/s",
+                   h2d_bytes_per_step=int(8 * (x_host.numel() + pert_host.numel() + noisy_host.numel())),
+                   d2h_bytes_per_step=int(8 * (out_host.numel() + eo_host.numel())))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    pk, pk_kind = peaks()
+    hbm = float(pk.get("hbm_gbs", PEAKS_FALLBACK["hbm_gbs"]))
+    cg_bytes = 112.0 * M * cg_member_iters          # spmv (48 B) + update (64 B) per active member-iteration
+    sat_bytes = 32.0 * M * sat_member_substeps      # read S, Vx, Vy, write S
+    cands = {
+        "k_cg_spmv+k_cg_update (one PCG iteration)": (cg_bytes, phase["cg"], stats_acc["cg_kernel_launches"] / 2),
+        "k_sat_substep": (sat_bytes, phase["saturation"], stats_acc["sat_kernel_launches"]),
+    }
+    dom = max(cands, key=lambda k: cands[k][1])
+    b, t_ms, n_launch = cands[dom]
+    achieved = b / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
+    roofline = dict(bound="hbm", kernel=dom, achieved=achieved, peak=hbm, unit="GB/s", frac=achieved / hbm,
+                    traffic=None, peak_source=pk_kind + (" burst" if pk_kind == "measured" else ""),
+                    algorithmic_bytes_per_launch=b / max(1, n_launch), avg_launch_ms=t_ms / max(1, n_launch),
+                    share_of_step=t_ms / ms)
+    other = "k_sat_substep" if dom != "k_sat_substep" else "k_cg_spmv+k_cg_update (one PCG iteration)"
+    ob, ot, _ = cands[other]
+
+    line = dict(
+        metric="ensemble forward-sim member*steps/s", value=value, unit="member*steps/s", n_gpus=world,
+        steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
+        vs_baseline=None, dtype="f64", data="synthetic",
+        config=dict(workload=wl["name"], grid=[wl["Nx"], wl["Ny"]], members_per_gpu=N_loc, members=N,
+                    nTime=wl["nTime"], p=p, update="ES (one ES-MDA pass, alpha=4)",
+                    l2="inputs larger than L2 (working set %.1f GB per GPU)" % (13 * N_loc * M * 8 / 1e9),
+                    parallelism=f"members sharded x{world}"),
+        update_ms=upd_ms / args.steps,
+        phases_ms_per_step={k: v / args.steps for k, v in phase.items()},
+        secondary_kernel=dict(kernel=other, achieved=(ob / (ot * 1e-3) / 1e9 if ot > 0 else 0.0), unit="GB/s"),
+        members_failed=bad, gpu_launches=int(launches), clocks=sampler.summary(), roofline=roofline,
+    )
+    if e2e:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline and world == 1:
+        v, cores, sample = cpu_forward_sample(wl, args.cpu_seconds)
+        line["cpu_baseline"] = dict(value=v, unit="member*steps/s", cores=cores, kind="port", sample=sample)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -59,6 +59,7 @@ SYMBOLS = {
     "hm_ctx_destroy": (C.c_int, [C.c_void_p]),
     "hm_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hm_synchronize": (C.c_int, [C.c_void_p]),
+    "hm_launch_count": (C.c_int, [C.c_void_p, C.POINTER(i64)]),
     "hm_sim_batch": (C.c_int, [C.c_void_p, C.POINTER(SimDesc)]),
     "hm_sim_batch_host": (C.c_int, [C.c_void_p, C.POINTER(SimDesc)]),
     "hm_sim_get_stats": (C.c_int, [C.c_void_p, C.POINTER(SimStats)]),
@@ -137,6 +138,11 @@ class Context:
 
         s = torch.cuda.current_stream(self.device).cuda_stream
         check(self.lib.hm_set_stream(self.handle, C.c_void_p(s)))
+
+    def launch_count(self) -> int:
+        n = i64()
+        check(self.lib.hm_launch_count(self.handle, C.byref(n)))
+        return int(n.value)
 
     def synchronize(self):
         check(self.lib.hm_synchronize(self.handle))

@@ -207,6 +207,7 @@ int whiten(hm_ctx* ctx, int64_t N, int64_t p, const double* Eo, const double* ob
     k_sub_mean<<<dim3((unsigned)((p + tb - 1) / tb), (unsigned)N), tb, 0, st>>>(N, p, Eo, p, tmp, p, mean, 1.0);
     HM_CHECK(hm::dgemm(ctx, false, false, N, p, p, 1.0, tmp, p, decorr, p, 0.0, S, p));
     k_innovation<<<(unsigned)((N * p + 255) / 256), 256, 0, st>>>(N, p, obs, Eo, perturbs, tmp);
+    ctx->launches += 3;
     HM_CHECK(hm::dgemm(ctx, false, false, N, p, p, 1.0, tmp, p, decorr, p, 0.0, D, p));
     *S_out = S;
     *D_out = D;
@@ -258,6 +259,7 @@ extern "C" int hm_center(hm_ctx* ctx, int64_t N, int64_t M, const double* E, int
     k_col_mean<<<gx, tb, 0, ctx->stream>>>(N, M, E, ldE, mu);
     const double scale = (rescale && N > 1) ? sqrt((double)N / (double)(N - 1)) : 1.0;
     k_sub_mean<<<dim3(gx, (unsigned)N), tb, 0, ctx->stream>>>(N, M, E, ldE, X, ldX, mu, scale);
+    ctx->launches += 2;
     HM_CUDA(cudaGetLastError());
     return HM_OK;
 }
@@ -269,6 +271,7 @@ extern "C" int hm_taper_bump(hm_ctx* ctx, int64_t M, int64_t p, const double* xy
     HM_CUDA(cudaSetDevice(ctx->device));
     k_taper_bump<<<(unsigned)((M * p + 255) / 256), 256, 0, ctx->stream>>>(M, p, xy_prm, xy_obs, radius,
                                                                             sharpness, out);
+    ctx->launches += 1;
     HM_CUDA(cudaGetLastError());
     return HM_OK;
 }
@@ -286,6 +289,7 @@ extern "C" int hm_es_update(hm_ctx* ctx, int64_t N, int64_t M, int64_t p, double
     // C = S^T S + (N-1) I
     HM_CHECK(hm::dgemm(ctx, true, false, p, p, N, 1.0, S, p, S, p, 0.0, C, p));
     k_add_diag<<<(unsigned)((p + 127) / 128), 128, 0, ctx->stream>>>(p, C, p, (double)(N - 1));
+    ctx->launches += 1;
     HM_CHECK(chol_factor(ctx, (int)p, C));
     // D <- D C^-1
     HM_CHECK(chol_solve_right(ctx, (int)p, C, (int)N, D));
@@ -337,6 +341,7 @@ extern "C" int hm_les_update(hm_ctx* ctx, int64_t N, int64_t M, int64_t p, doubl
     HM_CHECK(hm::dgemm(ctx, true, false, p, M, N, 1.0, S, p, E, ldE, 0.0, B, M));
     HM_CUDA(cudaFuncSetAttribute(k_local_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_local_analysis<<<(unsigned)M, 256, smem, ctx->stream>>>(M, (int)p, (double)(N - 1), A, taper, B, M, fail);
+    ctx->launches += 1;
     HM_CUDA(cudaGetLastError());
     HM_CHECK(hm::dgemm(ctx, false, false, N, M, p, 1.0, D, p, B, M, 1.0, E, ldE));
     return check_info(ctx, fail, "local analysis Cholesky");
@@ -393,6 +398,7 @@ extern "C" int hm_ies_step(hm_ctx* ctx, int64_t N, int64_t p, double* W, const d
     // dW = grad covw ; W += xStep dW   (HistoryMatch.py:941-942)
     HM_CHECK(chol_solve_right(ctx, (int)N, Cw, (int)N, G));
     k_axpy<<<(unsigned)((N * N + 255) / 256), 256, 0, st>>>(N * N, xStep, G, W);
+    ctx->launches += 5;  // set_identity, ies_resid, ies_grad_b, add_diag, axpy
     HM_CUDA(cudaGetLastError());
     return HM_OK;
 }

@@ -71,3 +71,9 @@ extern "C" int hm_synchronize(hm_ctx* ctx) {
     HM_CUDA(cudaStreamSynchronize(ctx->stream));
     return HM_OK;
 }
+
+extern "C" int hm_launch_count(hm_ctx* ctx, int64_t* out) {
+    HM_REQUIRE(ctx && out, "null");
+    *out = ctx->launches;
+    return HM_OK;
+}

@@ -100,5 +100,6 @@ struct hm_ctx {
     cusolverDnHandle_t solver = nullptr;
     int32_t* h_pinned = nullptr;  // small pinned scratch for device->host scalars
     hm_sim_stats sim_stats{};
+    int64_t launches = 0;  // kernels of this library launched on the ctx
     double phase_ms[5] = {0, 0, 0, 0, 0};
 };

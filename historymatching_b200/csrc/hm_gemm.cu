@@ -164,6 +164,7 @@ int launch(hm_ctx* ctx, const Operand& A, const Operand& B, int64_t K, double al
     dim3 grid((unsigned)((B.rows + BN - 1) / BN), (unsigned)((A.rows + BM - 1) / BM));
     k_dgemm<WM, WN><<<grid, WM * WN * 32, smem, ctx->stream>>>(A, B, K, alpha, beta, C, ldc);
     HM_CUDA(cudaGetLastError());
+    ctx->launches += 1;
     return HM_OK;
 }
 

@@ -730,6 +730,7 @@ extern "C" int hm_sim_batch(hm_ctx* ctx, const hm_sim_desc* desc) {
                                               : desc->n_members;
     for (int m0 = 0; m0 < desc->n_members; m0 += chunk)
         HM_CHECK(sim_chunk(ctx, *desc, m0, std::min(chunk, desc->n_members - m0)));
+    ctx->launches += ctx->sim_stats.kernel_launches;
     return HM_OK;
 }
 

@@ -50,6 +50,9 @@ int hm_ctx_destroy(hm_ctx* ctx);
 /* cudaStream_t passed as void*; NULL = the legacy default stream */
 int hm_set_stream(hm_ctx* ctx, void* cuda_stream);
 int hm_synchronize(hm_ctx* ctx);
+/* number of this library's kernels launched on the ctx since creation (its own kernels only,
+ * cuSOLVER calls are not counted) */
+int hm_launch_count(hm_ctx* ctx, int64_t* out);
 
 /* ---------------------------------------------------------------------------
  * Ensemble forward run.  Replaces, for a whole ensemble at once, the
