@@ -19,111 +19,18 @@
 //   k_cg_update    read x,r,p,Ap,dinv  write x,r,z               64 B / iteration
 //   k_flux_cfl     read P,TXl,TYl      write Vxl,Vyl             40 B / solve
 //   k_sat_substep  read S,Vxl,Vyl      write S'                  32 B / sub-step
-#include "hm_common.cuh"
+#include "hm_sim_common.cuh"
+
+using namespace hmsim;
+
+namespace hmsim {
+int pressure_solve(hm_ctx* ctx, const Geo& g, const Wells& w, int step, int nm, const double* TXl,
+                   const double* TYl, const double* dinv, const double* pin, double* P, double rtol,
+                   int max_iter, int precond, int* done, int* iters, int* counters, int* cg_batch,
+                   int* iters_used, bool* all_done_out);
+}
 
 namespace {
-
-constexpr int kThreads = 256;
-constexpr int kMaxWells = 64;
-constexpr int kTileCells = 2048;
-
-struct Geo {
-    int Nx, Ny, M;
-    int R;       // grid rows per tile
-    int nTiles;  // tiles per member
-    double cx;   // 2*hy/hx
-    double cy;   // 2*hx/hy
-    double h2;   // hx*hy
-    double vw, vo, swc, sor;
-};
-
-struct Wells {
-    int n;
-    const int32_t* cell;
-    int64_t cell_ms;
-    const double* rate;
-    int64_t rate_ms;
-    int64_t rate_ss;
-};
-
-// ---- small device helpers ---------------------------------------------------------------
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ double warp_min(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
-// Block-wide sum, result valid in thread 0.  `red` holds >= 32 doubles.
-__device__ __forceinline__ double block_sum(double v, double* red) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    v = warp_sum(v);
-    __syncthreads();
-    if (lane == 0) red[w] = v;
-    __syncthreads();
-    if (w == 0) {
-        v = (lane < (blockDim.x >> 5)) ? red[lane] : 0.0;
-        v = warp_sum(v);
-    }
-    return v;
-}
-__device__ __forceinline__ double block_min(double v, double* red) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    v = warp_min(v);
-    __syncthreads();
-    if (lane == 0) red[w] = v;
-    __syncthreads();
-    if (w == 0) {
-        v = (lane < (blockDim.x >> 5)) ? red[lane] : INFINITY;
-        v = warp_min(v);
-    }
-    return v;
-}
-
-// Deterministic sum of the per-tile partials of one member, computed
-// identically by every CTA of that member (so all tiles take the same
-// convergence decision and use the same alpha/beta).  Valid in all threads.
-__device__ __forceinline__ double sum_partials(const double* part, int n, double* bcast) {
-    if (threadIdx.x < 32) {
-        double v = 0.0;
-        for (int i = threadIdx.x; i < n; i += 32) v += part[i];
-        v = warp_sum(v);
-        if (threadIdx.x == 0) *bcast = v;
-    }
-    __syncthreads();
-    double out = *bcast;
-    __syncthreads();
-    return out;
-}
-
-__device__ __forceinline__ void load_wells(const Wells& w, int m, int step, int* wc, double* wr) {
-    for (int i = threadIdx.x; i < w.n; i += blockDim.x) {
-        wc[i] = w.cell[(int64_t)m * w.cell_ms + i];
-        wr[i] = w.rate[(int64_t)m * w.rate_ms + (int64_t)step * w.rate_ss + i];
-    }
-}
-// net source of cell c (wells sharing a cell accumulate, like np.add.at)
-__device__ __forceinline__ double cell_source(int c, int nw, const int* wc, const double* wr) {
-    double q = 0.0;
-    for (int i = 0; i < nw; ++i)
-        if (wc[i] == c) q += wr[i];
-    return q;
-}
-
-__device__ __forceinline__ double total_mobility(double s, const Geo& g) {
-    const double se = (s - g.swc) / (1.0 - g.swc - g.sor);
-    return se * se / g.vw + (1.0 - se) * (1.0 - se) / g.vo;
-}
-__device__ __forceinline__ double frac_flow(double s, const Geo& g) {
-    const double se = (s - g.swc) / (1.0 - g.swc - g.sor);
-    const double lw = se * se / g.vw;
-    const double lo = (1.0 - se) * (1.0 - se) / g.vo;
-    return lw / (lw + lo);
-}
 
 // ---- K1: mobility + harmonic transmissibilities (Appendix A.2) -------------------------------
 __global__ void __launch_bounds__(kThreads)
@@ -169,187 +76,6 @@ k_tpfa_setup(Geo g, const double* __restrict__ S, const double* __restrict__ K, 
         TXl[off + c] = txl;
         TYl[off + c] = tyl;
         dinv[off + c] = 1.0 / d;
-    }
-}
-
-// y = A x on one cell, x taken from the shared tile (li = local index incl. halo row)
-__device__ __forceinline__ double apply_A(const Geo& g, const double* xs, int li, int row, int col,
-                                          int c, const double* __restrict__ TXl,
-                                          const double* __restrict__ TYl, double pin) {
-    const double xc = xs[li];
-    const double txl = TXl[c];
-    const double tyl = TYl[c];
-    const double txh = row < g.Nx - 1 ? TXl[c + g.Ny] : 0.0;
-    const double tyh = col < g.Ny - 1 ? TYl[c + 1] : 0.0;
-    double y = txl * (xc - xs[li - g.Ny]);
-    y = fma(txh, xc - xs[li + g.Ny], y);
-    if (col > 0) y = fma(tyl, xc - xs[li - 1], y);
-    if (col < g.Ny - 1) y = fma(tyh, xc - xs[li + 1], y);
-    if (c == 0) y = fma(pin, xc, y);
-    return y;
-}
-
-// ---- K2a: r = q - A x0, z = r/diag; partial (r,z), (r,r) ------------------------------------
-__global__ void __launch_bounds__(kThreads)
-k_cg_init(Geo g, Wells w, int step, double* __restrict__ X, const double* __restrict__ TXl,
-          const double* __restrict__ TYl, const double* __restrict__ dinv,
-          const double* __restrict__ pin, double* __restrict__ Rv, double* __restrict__ Z,
-          double* __restrict__ part_rz, double* __restrict__ part_rr, double* __restrict__ bb,
-          int* __restrict__ done, int* __restrict__ iters, int* __restrict__ counters) {
-    extern __shared__ double sm[];
-    __shared__ int wc[kMaxWells];
-    __shared__ double wr[kMaxWells];
-    __shared__ double red[32];
-    const int m = blockIdx.x / g.nTiles, t = blockIdx.x % g.nTiles;
-    const int r0 = t * g.R, r1 = min(r0 + g.R, g.Nx), rows = r1 - r0;
-    const int64_t off = (int64_t)m * g.M;
-    load_wells(w, m, step, wc, wr);
-    for (int i = threadIdx.x; i < (rows + 2) * g.Ny; i += blockDim.x) {
-        const int row = r0 - 1 + i / g.Ny;
-        sm[i] = (row >= 0 && row < g.Nx) ? X[off + (int64_t)row * g.Ny + i % g.Ny] : 0.0;
-    }
-    __syncthreads();
-    // ||q||^2 with coincident wells merged
-    double q2 = 0.0;
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < w.n; ++i) {
-            bool first = true;
-            for (int j = 0; j < i; ++j) first = first && (wc[j] != wc[i]);
-            if (first) {
-                const double q = cell_source(wc[i], w.n, wc, wr);
-                q2 += q * q;
-            }
-        }
-        red[0] = q2;
-    }
-    __syncthreads();
-    q2 = red[0];
-    __syncthreads();
-    const double pinv = pin[m];
-    double rz = 0.0, rr = 0.0;
-    for (int i = threadIdx.x; i < rows * g.Ny; i += blockDim.x) {
-        const int li = i + g.Ny;
-        const int row = r0 + i / g.Ny, col = i % g.Ny, c = row * g.Ny + col;
-        double r, z;
-        if (q2 == 0.0) {  // no sources: the pinned system has the zero solution
-            X[off + c] = 0.0;
-            r = 0.0;
-            z = 0.0;
-        } else {
-            r = cell_source(c, w.n, wc, wr) - apply_A(g, sm, li, row, col, c, TXl + off, TYl + off, pinv);
-            z = r * dinv[off + c];
-        }
-        Rv[off + c] = r;
-        Z[off + c] = z;
-        rz = fma(r, z, rz);
-        rr = fma(r, r, rr);
-    }
-    rz = block_sum(rz, red);
-    rr = block_sum(rr, red);
-    if (threadIdx.x == 0) {
-        part_rz[(int64_t)m * g.nTiles + t] = rz;
-        part_rr[(int64_t)m * g.nTiles + t] = rr;
-        if (t == 0) {
-            bb[m] = q2;
-            iters[m] = 0;
-            const int d = (q2 == 0.0);
-            done[m] = d;
-            if (d) atomicAdd(&counters[0], 1);
-        }
-    }
-}
-
-// ---- K2b: p' = z + beta p; Ap' ; partial (p',Ap') ------------------------------------------
-// Parity buffers: iteration k reads partials[k&1] (written by update k-1 / init)
-// and p[k&1], writes p[(k+1)&1].
-__global__ void __launch_bounds__(kThreads)
-k_cg_spmv(Geo g, int k, double tol2, const double* __restrict__ Z, const double* __restrict__ Pin,
-          double* __restrict__ Pout, double* __restrict__ AP, const double* __restrict__ TXl,
-          const double* __restrict__ TYl, const double* __restrict__ pin,
-          const double* __restrict__ part_rz_cur, const double* __restrict__ part_rz_prev,
-          const double* __restrict__ part_rr_cur, double* __restrict__ part_pAp,
-          const double* __restrict__ bb, int* __restrict__ done, int* __restrict__ iters,
-          int* __restrict__ counters) {
-    extern __shared__ double sm[];
-    __shared__ double red[32];
-    __shared__ double bc;
-    const int m = blockIdx.x / g.nTiles, t = blockIdx.x % g.nTiles;
-    if (done[m]) return;
-    const double rr = sum_partials(part_rr_cur + (int64_t)m * g.nTiles, g.nTiles, &bc);
-    if (!(rr > tol2 * bb[m])) {  // converged (or NaN: stop, flagged later)
-        if (t == 0 && threadIdx.x == 0) {
-            done[m] = 1;
-            atomicAdd(&counters[0], 1);
-        }
-        return;
-    }
-    const double rz = sum_partials(part_rz_cur + (int64_t)m * g.nTiles, g.nTiles, &bc);
-    double beta = 0.0;
-    if (k > 0) beta = rz / sum_partials(part_rz_prev + (int64_t)m * g.nTiles, g.nTiles, &bc);
-
-    const int r0 = t * g.R, r1 = min(r0 + g.R, g.Nx), rows = r1 - r0;
-    const int64_t off = (int64_t)m * g.M;
-    for (int i = threadIdx.x; i < (rows + 2) * g.Ny; i += blockDim.x) {
-        const int row = r0 - 1 + i / g.Ny;
-        double pn = 0.0;
-        if (row >= 0 && row < g.Nx) {
-            const int64_t c = off + (int64_t)row * g.Ny + i % g.Ny;
-            pn = (k > 0) ? fma(beta, Pin[c], Z[c]) : Z[c];
-            if (row >= r0 && row < r1) Pout[c] = pn;
-        }
-        sm[i] = pn;
-    }
-    __syncthreads();
-    const double pinv = pin[m];
-    double pAp = 0.0;
-    for (int i = threadIdx.x; i < rows * g.Ny; i += blockDim.x) {
-        const int li = i + g.Ny;
-        const int row = r0 + i / g.Ny, col = i % g.Ny, c = row * g.Ny + col;
-        const double ap = apply_A(g, sm, li, row, col, c, TXl + off, TYl + off, pinv);
-        AP[off + c] = ap;
-        pAp = fma(sm[li], ap, pAp);
-    }
-    pAp = block_sum(pAp, red);
-    if (threadIdx.x == 0) {
-        part_pAp[(int64_t)m * g.nTiles + t] = pAp;
-        if (t == 0) iters[m] = k + 1;
-    }
-}
-
-// ---- K2c: x += a p; r -= a Ap; z = r/diag; partial (r,z), (r,r) ---------------------------------
-__global__ void __launch_bounds__(kThreads)
-k_cg_update(Geo g, double* __restrict__ X, double* __restrict__ Rv, double* __restrict__ Z,
-            const double* __restrict__ Pn, const double* __restrict__ AP,
-            const double* __restrict__ dinv, const double* __restrict__ part_rz_cur,
-            const double* __restrict__ part_pAp, double* __restrict__ part_rz_next,
-            double* __restrict__ part_rr_next, const int* __restrict__ done) {
-    __shared__ double red[32];
-    __shared__ double bc;
-    const int m = blockIdx.x / g.nTiles, t = blockIdx.x % g.nTiles;
-    if (done[m]) return;
-    const double rz = sum_partials(part_rz_cur + (int64_t)m * g.nTiles, g.nTiles, &bc);
-    const double pAp = sum_partials(part_pAp + (int64_t)m * g.nTiles, g.nTiles, &bc);
-    const double alpha = rz / pAp;
-    const int r0 = t * g.R, r1 = min(r0 + g.R, g.Nx);
-    const int64_t base = (int64_t)m * g.M + (int64_t)r0 * g.Ny;
-    const int n = (r1 - r0) * g.Ny;
-    double nrz = 0.0, nrr = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int64_t c = base + i;
-        const double pc = Pn[c];
-        X[c] = fma(alpha, pc, X[c]);
-        const double r = fma(-alpha, AP[c], Rv[c]);
-        const double z = r * dinv[c];
-        Rv[c] = r;
-        Z[c] = z;
-        nrz = fma(r, z, nrz);
-        nrr = fma(r, r, nrr);
-    }
-    nrz = block_sum(nrz, red);
-    nrr = block_sum(nrr, red);
-    if (threadIdx.x == 0) {
-        part_rz_next[(int64_t)m * g.nTiles + t] = nrz;
-        part_rr_next[(int64_t)m * g.nTiles + t] = nrr;
     }
 }
 
@@ -409,50 +135,130 @@ __global__ void k_substep_count(Geo g, int n_members, double dt, const double* _
 }
 
 // ---- K4: one explicit upwind sub-step (Appendix A.3) ---------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-k_sat_substep(Geo g, Wells w, int step, int it, double dt, const int* __restrict__ nts,
+// HBM-bound streaming kernel: 32 B per cell (S in, S out, the two low-face fluxes).
+// A thread owns CPT cells of the tile (linear index e = tid + j*kThreads, coalesced), keeps
+// their saturation in registers, publishes the fractional flow fw(S) of tile + 2 halo rows in
+// shared memory and then applies the upwind stencil.  Wells touch a handful of cells and are
+// applied as a fix-up pass after the sweep (the source terms are additive in the update).
+constexpr int kSatCPT = kTileCells / kThreads;
+
+struct Fluid {
+    double swc, inv_range, inv_vw, inv_vo;
+};
+// a / b for b well inside the float range: float reciprocal seed, two Newton steps and one
+// residual correction (no special-case branches; agrees with IEEE division to <= 1 ulp).
+__device__ __forceinline__ double fast_div(double a, double b) {
+    double r = (double)__frcp_rn((float)b);
+    r = r * fma(-b, r, 2.0);
+    r = r * fma(-b, r, 2.0);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
+__device__ __forceinline__ double frac_flow_fast(double s, const Fluid& f) {
+    const double se = (s - f.swc) * f.inv_range;
+    const double lw = se * se * f.inv_vw;
+    const double t = 1.0 - se;
+    const double lo = t * t * f.inv_vo;
+    return fast_div(lw, lw + lo);  // lw + lo >= min(1/vw,1/vo)/2 > 0 for every saturation
+}
+
+// The flux arrays carry a zero pad (Ny resp. 1 elements) behind the last member, and the low
+// faces of row 0 / column 0 are zero by construction, so the HIGH faces of the last row /
+// last column can be read as Vxl[c+Ny] / Vyl[c+1] without any boundary test.
+template <bool HAS_POR, bool FULL>
+__device__ __forceinline__ void sat_tile_body(const Geo& g, const Fluid& fl, int nInt, double hdt0, double dts,
+                                              const double* __restrict__ sp, double* __restrict__ op,
+                                              const double* __restrict__ vx, const double* __restrict__ vy,
+                                              const double* __restrict__ pp, double* fwp) {
+    const int Ny = g.Ny;
+    double s[kSatCPT];
+#pragma unroll
+    for (int j = 0; j < kSatCPT; ++j)
+        s[j] = (FULL || threadIdx.x + j * kThreads < nInt) ? sp[j * kThreads] : 0.0;
+#pragma unroll
+    for (int j = 0; j < kSatCPT; ++j)
+        if (FULL || threadIdx.x + j * kThreads < nInt) fwp[j * kThreads] = frac_flow_fast(s[j], fl);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kSatCPT; ++j) {
+        if (FULL || threadIdx.x + j * kThreads < nInt) {
+            const double vxl = vx[j * kThreads];
+            const double vyl = vy[j * kThreads];
+            const double vxh = vx[j * kThreads + Ny];
+            const double vyh = vy[j * kThreads + 1];
+            double hdt = hdt0;
+            if (HAS_POR) hdt = 0.5 * (dts / (g.h2 * pp[j * kThreads]));
+            const double* f = fwp + j * kThreads;
+            // B row: [x2(c-Ny), y2(c-1), diag, -y1(c+1), -x1(c+Ny)] scaled by dtx, with
+            // max(v,0) = (v+|v|)/2 and min(v,0) = (v-|v|)/2 (exact in floating point)
+            double acc = (hdt * (vxl + fabs(vxl))) * f[-Ny];
+            acc = fma(hdt * (vyl + fabs(vyl)), f[-1], acc);
+            const double dg = ((vyl - vyh) + (vxl - vxh)) - ((fabs(vyl) + fabs(vyh)) + (fabs(vxl) + fabs(vxh)));
+            acc = fma(hdt * dg, f[0], acc);
+            acc = fma(hdt * (fabs(vyh) - vyh), f[1], acc);
+            acc = fma(hdt * (fabs(vxh) - vxh), f[Ny], acc);
+            op[j * kThreads] = s[j] + acc;
+        }
+    }
+}
+
+template <bool HAS_POR>
+__global__ void __launch_bounds__(kThreads, 6)
+k_sat_substep(Geo g, Fluid fl, Wells w, int step, int it, double dt, const int* __restrict__ nts,
               const double* __restrict__ Sin, double* __restrict__ Sout,
               const double* __restrict__ Vxl, const double* __restrict__ Vyl,
               const double* __restrict__ por) {
-    extern __shared__ double sm[];  // fractional flow of tile + halo rows
+    extern __shared__ double fws[];  // fractional flow of tile + halo rows
     __shared__ int wc[kMaxWells];
     __shared__ double wr[kMaxWells];
     const int m = blockIdx.x / g.nTiles, t = blockIdx.x % g.nTiles;
     const int r0 = t * g.R, r1 = min(r0 + g.R, g.Nx), rows = r1 - r0;
-    const int64_t off = (int64_t)m * g.M;
+    const int Ny = g.Ny, nInt = rows * Ny;
+    const int64_t base = (int64_t)m * g.M + (int64_t)r0 * Ny;  // first interior cell
     const int n = nts[m];
+    // per-thread base pointers: element j of this thread sits at a compile-time offset j*kThreads
+    const double* __restrict__ sp = Sin + base + threadIdx.x;
+    double* __restrict__ op = Sout + base + threadIdx.x;
     if (it >= n) {  // this member needs fewer sub-steps: carry its state over
-        for (int i = threadIdx.x; i < rows * g.Ny; i += blockDim.x) {
-            const int64_t c = off + (int64_t)r0 * g.Ny + i;
-            Sout[c] = Sin[c];
-        }
+#pragma unroll
+        for (int j = 0; j < kSatCPT; ++j)
+            if (threadIdx.x + j * kThreads < nInt) op[j * kThreads] = sp[j * kThreads];
         return;
     }
-    load_wells(w, m, step, wc, wr);
-    for (int i = threadIdx.x; i < (rows + 2) * g.Ny; i += blockDim.x) {
-        const int row = r0 - 1 + i / g.Ny;
-        sm[i] = (row >= 0 && row < g.Nx) ? frac_flow(Sin[off + (int64_t)row * g.Ny + i % g.Ny], g) : 0.0;
+    if (w.n > 0) load_wells(w, m, step, wc, wr);
+    // halo rows (row r0-1 and row r1); outside the domain the value is never used (zero flux)
+    for (int e = threadIdx.x; e < 2 * Ny; e += kThreads) {
+        const bool lowh = e < Ny;
+        const int col = lowh ? e : e - Ny;
+        const int row = lowh ? r0 - 1 : r1;
+        double f = 0.0;
+        if (row >= 0 && row < g.Nx) f = frac_flow_fast(Sin[(int64_t)m * g.M + (int64_t)row * Ny + col], fl);
+        fws[lowh ? col : Ny + nInt + col] = f;
     }
-    __syncthreads();
     const double dts = dt / (double)n;
-    for (int i = threadIdx.x; i < rows * g.Ny; i += blockDim.x) {
-        const int li = i + g.Ny;
-        const int row = r0 + i / g.Ny, col = i % g.Ny, c = row * g.Ny + col;
-        const double vxl = Vxl[off + c];
-        const double vyl = Vyl[off + c];
-        const double vxh = row < g.Nx - 1 ? Vxl[off + c + g.Ny] : 0.0;
-        const double vyh = col < g.Ny - 1 ? Vyl[off + c + 1] : 0.0;
+    const double hdt0 = 0.5 * (dts / g.h2);
+    const double* __restrict__ vx = Vxl + base + threadIdx.x;
+    const double* __restrict__ vy = Vyl + base + threadIdx.x;
+    const double* __restrict__ pp = HAS_POR ? por + (int64_t)r0 * Ny + threadIdx.x : nullptr;
+    double* fwp = fws + Ny + threadIdx.x;
+    if (nInt == kTileCells)
+        sat_tile_body<HAS_POR, true>(g, fl, nInt, hdt0, dts, sp, op, vx, vy, pp, fwp);
+    else
+        sat_tile_body<HAS_POR, false>(g, fl, nInt, hdt0, dts, sp, op, vx, vy, pp, fwp);
+    if (w.n == 0) return;
+    __syncthreads();
+    // well fix-up: S += dtx * (min(q,0) * fw(S) + max(q,0)) on the cells that hold wells
+    for (int i = threadIdx.x; i < w.n; i += kThreads) {
+        const int c = wc[i];
+        const int e = c - r0 * Ny;
+        if (e < 0 || e >= nInt) continue;
+        bool first = true;
+        for (int k = 0; k < i; ++k) first = first && (wc[k] != c);
+        if (!first) continue;
         const double q = cell_source(c, w.n, wc, wr);
-        const double fi = fmax(q, 0.0), fp = fmin(q, 0.0);
-        const double dtx = dts / (g.h2 * (por ? por[c] : 1.0));
-        // B row: [x2(c-Ny), y2(c-1), diag, -y1(c+1), -x1(c+Ny)] scaled by dtx
-        double acc = (dtx * fmax(vxl, 0.0)) * sm[li - g.Ny];
-        if (col > 0) acc = fma(dtx * fmax(vyl, 0.0), sm[li - 1], acc);
-        const double diag = fp + fmin(vyl, 0.0) - fmax(vyh, 0.0) + fmin(vxl, 0.0) - fmax(vxh, 0.0);
-        acc = fma(dtx * diag, sm[li], acc);
-        if (col < g.Ny - 1) acc = fma(dtx * -fmin(vyh, 0.0), sm[li + 1], acc);
-        acc = fma(dtx * -fmin(vxh, 0.0), sm[li + g.Ny], acc);
-        Sout[off + c] = Sin[off + c] + (acc + fi * dtx);
+        double dtx = dts / g.h2;
+        if (HAS_POR) dtx = dts / (g.h2 * por[c]);
+        Sout[base + e] += fma(dtx * fmin(q, 0.0), fws[Ny + e], fmax(q, 0.0) * dtx);
     }
 }
 
@@ -529,6 +335,7 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
     g.Ny = d.Ny;
     g.M = d.Nx * d.Ny;
     g.R = std::max(1, std::min(d.Nx, kTileCells / d.Ny));
+    if (g.R < d.Nx && g.R > 1) g.R &= ~1;  // even tile height: 2x2 multigrid aggregates never straddle tiles
     g.nTiles = (d.Nx + g.R - 1) / g.R;
     const double hx = d.Lx / d.Nx, hy = d.Ly / d.Ny;
     g.cx = 2 * hy / hx;
@@ -538,31 +345,27 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
     g.vo = d.vo;
     g.swc = d.swc;
     g.sor = d.sor;
+    Fluid fl;
+    fl.swc = d.swc;
+    fl.inv_range = 1.0 / (1.0 - d.swc - d.sor);
+    fl.inv_vw = 1.0 / d.vw;
+    fl.inv_vo = 1.0 / d.vo;
     const int64_t M = g.M;
     const size_t vec = (size_t)nm * M;
     const size_t nPart = (size_t)nm * g.nTiles;
 
-    double *TXl, *TYl, *dinv, *P, *Rv, *Z, *AP, *Pa, *Pb, *Vxl, *Vyl, *Sa, *Sb;
-    double *part_rz, *part_rr, *part_pAp, *part_pm, *bb, *pin;
+    double *TXl, *TYl, *dinv, *P, *Vxl, *Vyl, *Sa, *Sb;
+    double *part_pm, *pin;
     int *done, *iters, *nts, *cg_fail, *counters;
     HM_CHECK(ctx->ws.get("sim.TXl", vec, &TXl));
     HM_CHECK(ctx->ws.get("sim.TYl", vec, &TYl));
     HM_CHECK(ctx->ws.get("sim.dinv", vec, &dinv));
     HM_CHECK(ctx->ws.get("sim.P", vec, &P));
-    HM_CHECK(ctx->ws.get("sim.r", vec, &Rv));
-    HM_CHECK(ctx->ws.get("sim.z", vec, &Z));
-    HM_CHECK(ctx->ws.get("sim.Ap", vec, &AP));
-    HM_CHECK(ctx->ws.get("sim.pa", vec, &Pa));
-    HM_CHECK(ctx->ws.get("sim.pb", vec, &Pb));
-    HM_CHECK(ctx->ws.get("sim.Vxl", vec, &Vxl));
-    HM_CHECK(ctx->ws.get("sim.Vyl", vec, &Vyl));
+    HM_CHECK(ctx->ws.get("sim.Vxl", vec + (size_t)d.Ny, &Vxl));  // + zero pad, see sat_tile_body
+    HM_CHECK(ctx->ws.get("sim.Vyl", vec + 1, &Vyl));
     HM_CHECK(ctx->ws.get("sim.Sa", vec, &Sa));
     HM_CHECK(ctx->ws.get("sim.Sb", vec, &Sb));
-    HM_CHECK(ctx->ws.get("sim.part_rz", 2 * nPart, &part_rz));
-    HM_CHECK(ctx->ws.get("sim.part_rr", 2 * nPart, &part_rr));
-    HM_CHECK(ctx->ws.get("sim.part_pAp", nPart, &part_pAp));
     HM_CHECK(ctx->ws.get("sim.part_pm", nPart, &part_pm));
-    HM_CHECK(ctx->ws.get("sim.bb", (size_t)nm, &bb));
     HM_CHECK(ctx->ws.get("sim.pin", (size_t)nm, &pin));
     HM_CHECK(ctx->ws.get("sim.done", (size_t)nm, &done));
     HM_CHECK(ctx->ws.get("sim.iters", (size_t)nm, &iters));
@@ -585,7 +388,6 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
     int32_t* cg_iters_out = d.cg_iters ? d.cg_iters + (int64_t)m0 * d.n_steps : nullptr;
 
     const double rtol = d.cg_rtol > 0 ? d.cg_rtol : 1e-12;
-    const double tol2 = rtol * rtol;
     const int max_iter = d.cg_max_iter > 0 ? d.cg_max_iter : 100 * (d.Nx + d.Ny) + 200;
 
     const int grid = nm * g.nTiles;
@@ -595,10 +397,9 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
         HM_CUDA(cudaFuncSetAttribute(k_tpfa_setup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     }
     if (smem1 > 48 * 1024) {
-        HM_CUDA(cudaFuncSetAttribute(k_cg_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-        HM_CUDA(cudaFuncSetAttribute(k_cg_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
         HM_CUDA(cudaFuncSetAttribute(k_flux_cfl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-        HM_CUDA(cudaFuncSetAttribute(k_sat_substep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        HM_CUDA(cudaFuncSetAttribute(k_sat_substep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        HM_CUDA(cudaFuncSetAttribute(k_sat_substep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     }
     const int copy_blocks = (int)((vec + 255) / 256);
 
@@ -606,6 +407,8 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
     k_copy_rows<<<copy_blocks, 256, 0, st>>>(nm, (int)M, d.S0 + (int64_t)m0 * d.S0_member_stride,
                                               d.S0_member_stride, Sa, M);
     HM_CUDA(cudaMemsetAsync(P, 0, vec * sizeof(double), st));
+    HM_CUDA(cudaMemsetAsync(Vxl + vec, 0, (size_t)d.Ny * sizeof(double), st));
+    HM_CUDA(cudaMemsetAsync(Vyl + vec, 0, sizeof(double), st));
     HM_CUDA(cudaMemsetAsync(cg_fail, 0, nm * sizeof(int), st));
     if (S_hist) k_copy_rows<<<copy_blocks, 256, 0, st>>>(nm, (int)M, Sa, M, S_hist, (int64_t)(d.n_steps + 1) * M);
     ctx->sim_stats.kernel_launches += 1 + (S_hist ? 1 : 0);
@@ -613,49 +416,20 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
     PhaseTimer timer(st);
     double* Scur = Sa;
     double* Snxt = Sb;
-    int cg_batch = 32;
+    int cg_batch = d.precond == 1 ? 32 : 8;
     for (int step = 0; step < d.n_steps; ++step) {
         timer.mark(0);
         k_tpfa_setup<<<grid, kThreads, smem2, st>>>(g, Scur, K, d.K_member_stride, d.K_comp_stride, TXl,
                                                      TYl, dinv, pin);
         timer.mark(1);
         HM_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(int), st));
-        k_cg_init<<<grid, kThreads, smem1, st>>>(g, w, step, P, TXl, TYl, dinv, pin, Rv, Z, part_rz,
-                                                  part_rr, bb, done, iters, counters);
-        ctx->sim_stats.kernel_launches += 2;
         int k = 0;
         bool all_done = false;
-        while (k < max_iter && !all_done) {
-            const int kend = std::min(max_iter, k + cg_batch);
-            for (; k < kend; ++k) {
-                const int cur = k & 1, nxt = cur ^ 1;
-                double* Pin = cur ? Pb : Pa;
-                double* Pout = cur ? Pa : Pb;
-                k_cg_spmv<<<grid, kThreads, smem1, st>>>(g, k, tol2, Z, Pin, Pout, AP, TXl, TYl, pin,
-                                                          part_rz + cur * nPart, part_rz + nxt * nPart,
-                                                          part_rr + cur * nPart, part_pAp, bb, done,
-                                                          iters, counters);
-                k_cg_update<<<grid, kThreads, 0, st>>>(g, P, Rv, Z, Pout, AP, dinv, part_rz + cur * nPart,
-                                                        part_pAp, part_rz + nxt * nPart,
-                                                        part_rr + nxt * nPart, done);
-            }
-            HM_CUDA(cudaMemcpyAsync(ctx->h_pinned, counters, sizeof(int), cudaMemcpyDeviceToHost, st));
-            HM_CUDA(cudaStreamSynchronize(st));
-            all_done = ctx->h_pinned[0] >= nm;
-        }
-        if (!all_done) {
-            // one more convergence test (the last update may have converged), then flag the rest
-            const int cur = k & 1, nxt = cur ^ 1;
-            k_cg_spmv<<<grid, kThreads, smem1, st>>>(g, k, tol2, Z, cur ? Pb : Pa, cur ? Pa : Pb, AP, TXl,
-                                                      TYl, pin, part_rz + cur * nPart,
-                                                      part_rz + nxt * nPart, part_rr + cur * nPart,
-                                                      part_pAp, bb, done, iters, counters);
-        }
+        HM_CHECK(pressure_solve(ctx, g, w, step, nm, TXl, TYl, dinv, pin, P, rtol, max_iter, d.precond, done, iters,
+                                counters, &cg_batch, &k, &all_done));
+        ctx->sim_stats.kernel_launches += 1;
         if (cg_iters_out)
             k_record_iters<<<(nm + 127) / 128, 128, 0, st>>>(nm, iters, cg_iters_out, d.n_steps, step);
-        ctx->sim_stats.cg_iterations += k;
-        ctx->sim_stats.kernel_launches += 2 * k;
-        ctx->sim_stats.cg_kernel_launches += 2 * k + 1;
 
         timer.mark(2);
         k_flux_cfl<<<grid, kThreads, smem1, st>>>(g, w, step, P, TXl, TYl, d.por, Vxl, Vyl, part_pm);
@@ -668,8 +442,12 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
 
         timer.mark(3);
         for (int it = 0; it < max_nts; ++it) {
-            k_sat_substep<<<grid, kThreads, smem1, st>>>(g, w, step, it, d.dt, nts, Scur, Snxt, Vxl, Vyl,
-                                                          d.por);
+            if (d.por)
+                k_sat_substep<true><<<grid, kThreads, smem1, st>>>(g, fl, w, step, it, d.dt, nts, Scur, Snxt,
+                                                                    Vxl, Vyl, d.por);
+            else
+                k_sat_substep<false><<<grid, kThreads, smem1, st>>>(g, fl, w, step, it, d.dt, nts, Scur, Snxt,
+                                                                     Vxl, Vyl, nullptr);
             std::swap(Scur, Snxt);
         }
         ctx->sim_stats.sat_substeps += max_nts;
@@ -687,8 +465,6 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
                                                       (int64_t)(d.n_steps + 1) * M);
             ctx->sim_stats.kernel_launches += 1;
         }
-        // adapt the convergence-check cadence to what this step needed
-        cg_batch = std::max(8, std::min(64, k / 6 + 4));
         if (!all_done) {
             k_mark_unconverged<<<(nm + 127) / 128, 128, 0, st>>>(nm, done, cg_fail);
         }
@@ -714,7 +490,8 @@ int validate(const hm_sim_desc& d) {
     HM_REQUIRE(d.n_wells == 0 || (d.well_cell && d.well_rate), "well arrays");
     HM_REQUIRE(d.n_steps >= 0 && d.dt > 0, "dt, n_steps");
     HM_REQUIRE(d.n_obs == 0 || d.obs_cell, "obs_cell");
-    HM_REQUIRE((size_t)(d.Ny) * 3 * sizeof(double) * 2 <= 200 * 1024, "Ny too large for the row tile");
+    HM_REQUIRE(d.Ny <= 1024, "Ny <= 1024 (row tiles of at least two grid rows must fit 2048 cells)");
+    HM_REQUIRE(d.precond >= 0 && d.precond <= 2, "precond: 0 = multigrid V-cycle, 1 = Jacobi, 2 = multigrid W-cycle");
     return HM_OK;
 }
 

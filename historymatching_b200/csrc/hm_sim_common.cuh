@@ -1,0 +1,111 @@
+// Device helpers shared by the simulator kernels (hm_pressure.cu, hm_sim.cu).
+#pragma once
+
+#include "hm_common.cuh"
+
+namespace hmsim {
+
+constexpr int kThreads = 256;
+constexpr int kMaxWells = 64;
+constexpr int kTileCells = 2048;
+
+struct Geo {
+    int Nx, Ny, M;
+    int R;       // grid rows per tile
+    int nTiles;  // tiles per member
+    double cx;   // 2*hy/hx
+    double cy;   // 2*hx/hy
+    double h2;   // hx*hy
+    double vw, vo, swc, sor;
+};
+
+struct Wells {
+    int n;
+    const int32_t* cell;
+    int64_t cell_ms;
+    const double* rate;
+    int64_t rate_ms;
+    int64_t rate_ss;
+};
+
+// ---- small device helpers ---------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum, result valid in thread 0.  `red` holds >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = (lane < (blockDim.x >> 5)) ? red[lane] : 0.0;
+        v = warp_sum(v);
+    }
+    return v;
+}
+__device__ __forceinline__ double block_min(double v, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_min(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = (lane < (blockDim.x >> 5)) ? red[lane] : INFINITY;
+        v = warp_min(v);
+    }
+    return v;
+}
+
+// Deterministic sum of the per-tile partials of one member, computed
+// identically by every CTA of that member (so all tiles take the same
+// convergence decision and use the same alpha/beta).  Valid in all threads.
+__device__ __forceinline__ double sum_partials(const double* part, int n, double* bcast) {
+    if (threadIdx.x < 32) {
+        double v = 0.0;
+        for (int i = threadIdx.x; i < n; i += 32) v += part[i];
+        v = warp_sum(v);
+        if (threadIdx.x == 0) *bcast = v;
+    }
+    __syncthreads();
+    double out = *bcast;
+    __syncthreads();
+    return out;
+}
+
+__device__ __forceinline__ void load_wells(const Wells& w, int m, int step, int* wc, double* wr) {
+    for (int i = threadIdx.x; i < w.n; i += blockDim.x) {
+        wc[i] = w.cell[(int64_t)m * w.cell_ms + i];
+        wr[i] = w.rate[(int64_t)m * w.rate_ms + (int64_t)step * w.rate_ss + i];
+    }
+}
+// net source of cell c (wells sharing a cell accumulate, like np.add.at)
+__device__ __forceinline__ double cell_source(int c, int nw, const int* wc, const double* wr) {
+    double q = 0.0;
+    for (int i = 0; i < nw; ++i)
+        if (wc[i] == c) q += wr[i];
+    return q;
+}
+
+__device__ __forceinline__ double total_mobility(double s, const Geo& g) {
+    const double se = (s - g.swc) / (1.0 - g.swc - g.sor);
+    return se * se / g.vw + (1.0 - se) * (1.0 - se) / g.vo;
+}
+__device__ __forceinline__ double frac_flow(double s, const Geo& g) {
+    const double se = (s - g.swc) / (1.0 - g.swc - g.sor);
+    const double lw = se * se / g.vw;
+    const double lo = (1.0 - se) * (1.0 - se) / g.vo;
+    return lw / (lw + lo);
+}
+
+
+}  // namespace hmsim

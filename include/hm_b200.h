@@ -100,7 +100,7 @@ typedef struct hm_sim_desc {
     double cg_rtol;      /* <=0: default 1e-12 (||r|| <= rtol ||q||) */
     int32_t cg_max_iter; /* <=0: default 100*(Nx+Ny)+200 */
     int32_t chunk_members; /* <=0: all members in one launch wave */
-    int32_t reserved;
+    int32_t precond;       /* pressure preconditioner: 0 = multigrid V-cycle (default), 1 = Jacobi, 2 = multigrid W-cycle */
 } hm_sim_desc;
 
 /* statistics of the last hm_sim_batch on this ctx (host side) */
