@@ -49,18 +49,18 @@ struct Lvl {
     double* xb;       // iterate after post-smoothing = the level's result (level 0: z)
 };
 
-// (A x) at local cell (row, col); xs is a shared tile whose row `row` starts at xs_row.
-__device__ __forceinline__ double stencil(const Lvl& L, const double* xs_row, int row, int col, int c,
-                                          const double* __restrict__ TX, const double* __restrict__ TY,
-                                          double pin) {
-    const int ny = L.ny;
-    const double xc = xs_row[col];
-    double y = 0.0;
-    if (row > 0) y = TX[c] * (xc - xs_row[col - ny]);
-    if (row < L.nx - 1) y = fma(TX[c + ny], xc - xs_row[col + ny], y);
-    if (col > 0) y = fma(TY[c], xc - xs_row[col - 1], y);
-    if (col < ny - 1) y = fma(TY[c + 1], xc - xs_row[col + 1], y);
-    if (c == 0) y = fma(pin, xc, y);
+// (A x) at one cell.  xr points at the cell's row in a shared tile that has valid (finite) rows
+// above and below; Tx / Ty point at the cell's own low-face transmissibilities.  No boundary
+// tests: boundary faces carry T = 0 and every T array has a zero pad behind the last member, so
+// the high faces Tx[ny] / Ty[1] are always readable and vanish where there is no neighbour.
+__device__ __forceinline__ double stencil(const double* xr, int col, int ny, const double* __restrict__ Tx,
+                                          const double* __restrict__ Ty, bool cell0, double pin) {
+    const double xc = xr[col];
+    double y = Tx[0] * (xc - xr[col - ny]);
+    y = fma(Tx[ny], xc - xr[col + ny], y);
+    y = fma(Ty[0], xc - xr[col - 1], y);
+    y = fma(Ty[1], xc - xr[col + 1], y);
+    if (cell0) y = fma(pin, xc, y);
     return y;
 }
 
@@ -94,15 +94,16 @@ __global__ void k_mg_coarsen(int nm, Lvl f, int cnx, int cny, double* __restrict
 }
 
 // ---- streamed level: pre-smoothing + residual + restriction --------------------------------------
-// Rows [r0,r1) of the tile (r0 even).  x1 = w D^-1 b on rows [r0-2, r1+2), x2 = x1 + w D^-1 (b - A x1)
+// Rows [r0,r1) of the tile (r0 even).  x1 = w1 D^-1 b on rows [r0-2, r1+2), x2 = x1 + w2 D^-1 (b - A x1)
 // on rows [r0-1, r1+1), residual on the tile rows, 2x2 sums of it to the coarse right-hand side.
+// A warp walks whole grid rows (lanes along the contiguous index): no integer division.
 __global__ void __launch_bounds__(kThreads)
 k_mg_down(Lvl f, int cny, double* __restrict__ cb, const double* __restrict__ pin,
           const int* __restrict__ done) {
     extern __shared__ double sm[];
     const int m = blockIdx.x / f.nTiles, t = blockIdx.x % f.nTiles;
     if (done[m]) return;
-    const int ny = f.ny;
+    const int ny = f.ny, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nW = kThreads >> 5;
     const int r0 = t * f.R, r1 = min(r0 + f.R, f.nx), rows = r1 - r0;
     const int64_t off = (int64_t)m * f.M;
     const double* __restrict__ b = f.b + off;
@@ -112,46 +113,55 @@ k_mg_down(Lvl f, int cny, double* __restrict__ cb, const double* __restrict__ pi
     const double pinv = pin[m];
     double* x1 = sm;                     // rows r0-2 .. r1+1   -> (rows+4) * ny
     double* x2 = sm + (f.R + 4) * ny;    // rows r0-1 .. r1     -> (rows+2) * ny
-    for (int i = threadIdx.x; i < (rows + 4) * ny; i += kThreads) {
-        const int row = r0 - 2 + i / ny, col = i % ny;
-        double v = 0.0;
-        if (row >= 0 && row < f.nx) {
-            const int c = row * ny + col;
-            v = kW1 * dinv[c] * b[c];
-        }
-        x1[i] = v;
+    for (int lr = warp; lr < rows + 4; lr += nW) {
+        const int row = r0 - 2 + lr;
+        const bool in = row >= 0 && row < f.nx;
+        const int c0 = row * ny;
+        for (int col = lane; col < ny; col += 32) x1[lr * ny + col] = in ? kW1 * dinv[c0 + col] * b[c0 + col] : 0.0;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < (rows + 2) * ny; i += kThreads) {
-        const int row = r0 - 1 + i / ny, col = i % ny;
-        double v = 0.0;
-        if (row >= 0 && row < f.nx) {
-            const int c = row * ny + col;
-            const double* xr = x1 + (i / ny + 1) * ny;
-            v = xr[col] + kW2 * dinv[c] * (b[c] - stencil(f, xr, row, col, c, TX, TY, pinv));
+    for (int lr = warp; lr < rows + 2; lr += nW) {
+        const int row = r0 - 1 + lr;
+        const bool in = row >= 0 && row < f.nx;
+        const int c0 = row * ny;
+        const double* xr = x1 + (lr + 1) * ny;
+        for (int col = lane; col < ny; col += 32) {
+            double v = 0.0;
+            if (in) {
+                const int c = c0 + col;
+                v = xr[col] + kW2 * dinv[c] * (b[c] - stencil(xr, col, ny, TX + c, TY + c, c == 0, pinv));
+            }
+            x2[lr * ny + col] = v;
         }
-        x2[i] = v;
     }
     __syncthreads();
     double* res = x1;  // x1 is dead: reuse for the residual of the tile rows, index (row-r0)*ny+col
-    for (int i = threadIdx.x; i < rows * ny; i += kThreads) {
-        const int lr = i / ny, col = i % ny, row = r0 + lr, c = row * ny + col;
+    for (int lr = warp; lr < rows; lr += nW) {
+        const int c0 = (r0 + lr) * ny;
         const double* xr = x2 + (lr + 1) * ny;
-        f.xa[off + c] = xr[col];
-        res[i] = b[c] - stencil(f, xr, row, col, c, TX, TY, pinv);
+        for (int col = lane; col < ny; col += 32) {
+            const int c = c0 + col;
+            f.xa[off + c] = xr[col];
+            res[lr * ny + col] = b[c] - stencil(xr, col, ny, TX + c, TY + c, c == 0, pinv);
+        }
     }
     __syncthreads();
     const int crows = (rows + 1) / 2, cM = ((f.nx + 1) / 2) * cny;
-    for (int i = threadIdx.x; i < crows * cny; i += kThreads) {
-        const int I = i / cny, J = i % cny;
-        const int lr = 2 * I, col = 2 * J;
-        double s = res[lr * ny + col];
-        if (col + 1 < ny) s += res[lr * ny + col + 1];
-        if (lr + 1 < rows) {
-            s += res[(lr + 1) * ny + col];
-            if (col + 1 < ny) s += res[(lr + 1) * ny + col + 1];
+    for (int I = warp; I < crows; I += nW) {
+        const int lr = 2 * I;
+        const bool two = lr + 1 < rows;
+        double* out = cb + (int64_t)m * cM + (int64_t)(r0 / 2 + I) * cny;
+        for (int J = lane; J < cny; J += 32) {
+            const int col = 2 * J;
+            const bool cc = col + 1 < ny;
+            double sacc = res[lr * ny + col];
+            if (cc) sacc += res[lr * ny + col + 1];
+            if (two) {
+                sacc += res[(lr + 1) * ny + col];
+                if (cc) sacc += res[(lr + 1) * ny + col + 1];
+            }
+            out[J] = sacc;
         }
-        cb[(int64_t)m * cM + (int64_t)(r0 / 2 + I) * cny + J] = s;
     }
 }
 
@@ -164,7 +174,7 @@ k_mg_up(Lvl f, int cny, const double* __restrict__ cx, const double* __restrict_
     __shared__ double red[32];
     const int m = blockIdx.x / f.nTiles, t = blockIdx.x % f.nTiles;
     if (done[m]) return;
-    const int ny = f.ny;
+    const int ny = f.ny, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nW = kThreads >> 5;
     const int r0 = t * f.R, r1 = min(r0 + f.R, f.nx), rows = r1 - r0;
     const int64_t off = (int64_t)m * f.M;
     const int cM = ((f.nx + 1) / 2) * cny;
@@ -177,32 +187,40 @@ k_mg_up(Lvl f, int cny, const double* __restrict__ cx, const double* __restrict_
     const double pinv = pin[m];
     double* x0 = sm;                     // rows r0-2 .. r1+1
     double* x3 = sm + (f.R + 4) * ny;    // rows r0-1 .. r1
-    for (int i = threadIdx.x; i < (rows + 4) * ny; i += kThreads) {
-        const int row = r0 - 2 + i / ny, col = i % ny;
-        double v = 0.0;
-        if (row >= 0 && row < f.nx) v = xa[row * ny + col] + xc[(row >> 1) * cny + (col >> 1)];
-        x0[i] = v;
+    for (int lr = warp; lr < rows + 4; lr += nW) {
+        const int row = r0 - 2 + lr;
+        const bool in = row >= 0 && row < f.nx;
+        const double* xar = xa + row * ny;
+        const double* xcr = xc + (row >> 1) * cny;
+        for (int col = lane; col < ny; col += 32) x0[lr * ny + col] = in ? xar[col] + xcr[col >> 1] : 0.0;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < (rows + 2) * ny; i += kThreads) {
-        const int row = r0 - 1 + i / ny, col = i % ny;
-        double v = 0.0;
-        if (row >= 0 && row < f.nx) {
-            const int c = row * ny + col;
-            const double* xr = x0 + (i / ny + 1) * ny;
-            v = xr[col] + kW2 * dinv[c] * (b[c] - stencil(f, xr, row, col, c, TX, TY, pinv));
+    for (int lr = warp; lr < rows + 2; lr += nW) {
+        const int row = r0 - 1 + lr;
+        const bool in = row >= 0 && row < f.nx;
+        const int c0 = row * ny;
+        const double* xr = x0 + (lr + 1) * ny;
+        for (int col = lane; col < ny; col += 32) {
+            double v = 0.0;
+            if (in) {
+                const int c = c0 + col;
+                v = xr[col] + kW2 * dinv[c] * (b[c] - stencil(xr, col, ny, TX + c, TY + c, c == 0, pinv));
+            }
+            x3[lr * ny + col] = v;
         }
-        x3[i] = v;
     }
     __syncthreads();
     double dot = 0.0;
-    for (int i = threadIdx.x; i < rows * ny; i += kThreads) {
-        const int lr = i / ny, col = i % ny, row = r0 + lr, c = row * ny + col;
+    for (int lr = warp; lr < rows; lr += nW) {
+        const int c0 = (r0 + lr) * ny;
         const double* xr = x3 + (lr + 1) * ny;
-        const double bc = b[c];
-        const double v = xr[col] + kW1 * dinv[c] * (bc - stencil(f, xr, row, col, c, TX, TY, pinv));
-        f.xb[off + c] = v;
-        if (DOT) dot = fma(bc, v, dot);
+        for (int col = lane; col < ny; col += 32) {
+            const int c = c0 + col;
+            const double bc = b[c];
+            const double v = xr[col] + kW1 * dinv[c] * (bc - stencil(xr, col, ny, TX + c, TY + c, c == 0, pinv));
+            f.xb[off + c] = v;
+            if (DOT) dot = fma(bc, v, dot);
+        }
     }
     if (DOT) {
         dot = block_sum(dot, red);
@@ -272,66 +290,52 @@ __device__ __forceinline__ void onchip_smooth(const OnchipMeta& mt, const Onchip
     }
 }
 
-template <int I>
-__device__ __noinline__ void onchip_cycle(const OnchipMeta& mt, OnchipSmem s, double pin) {
-    const int l = I;
-    const int M = mt.M[l], ny = mt.ny[l], o = mt.off[l];
-    if (l == mt.n - 1) {  // coarsest level of the hierarchy
-        if (M == 1) {
-            if (threadIdx.x == 0) s.X[o] = s.B[o] * s.DV[o];
-            __syncthreads();
-        } else {
-            onchip_smooth(mt, s, l, pin, 8, kW1, kW2);
-        }
-        return;
-    }
-    if constexpr (I + 1 < kMaxLevels) {
-        onchip_smooth(mt, s, l, pin, 2, kW1, kW2);
-        // residual restricted to the next level (each coarse thread evaluates its own children)
-        const int cM = mt.M[l + 1], cny = mt.ny[l + 1], co = mt.off[l + 1], nx = mt.nx[l];
-        const float cinv = mt.inv_ny[l + 1];
-        for (int e = threadIdx.x; e < cM; e += kOnchipThreads) {
-            int ci, cj;
-            cell_ij(e, cny, cinv, ci, cj);
-            double r = 0.0;
+// Residual of level l restricted to level l+1 (each coarse thread evaluates its own children);
+// the coarse iterate is reset to zero.
+__device__ __forceinline__ void onchip_restrict(const OnchipMeta& mt, const OnchipSmem& s, int l, double pin) {
+    const int ny = mt.ny[l], nx = mt.nx[l], o = mt.off[l];
+    const int cM = mt.M[l + 1], cny = mt.ny[l + 1], co = mt.off[l + 1];
+    const float cinv = mt.inv_ny[l + 1];
+    for (int e = threadIdx.x; e < cM; e += kOnchipThreads) {
+        int ci, cj;
+        cell_ij(e, cny, cinv, ci, cj);
+        double r = 0.0;
 #pragma unroll
-            for (int di = 0; di < 2; ++di)
+        for (int di = 0; di < 2; ++di)
 #pragma unroll
-                for (int dj = 0; dj < 2; ++dj) {
-                    const int i = 2 * ci + di, j = 2 * cj + dj;
-                    if (i < nx && j < ny) {
-                        const int fe = i * ny + j;
-                        r += s.B[o + fe] - onchip_Ax(mt, s, l, fe, i, j, pin);
-                    }
+            for (int dj = 0; dj < 2; ++dj) {
+                const int i = 2 * ci + di, j = 2 * cj + dj;
+                if (i < nx && j < ny) {
+                    const int fe = i * ny + j;
+                    r += s.B[o + fe] - onchip_Ax(mt, s, l, fe, i, j, pin);
                 }
-            s.B[co + e] = r;
-            s.X[co + e] = 0.0;
-        }
-        __syncthreads();
-        onchip_cycle<I + 1>(mt, s, pin);
-        if (cM >= mt.wmin) onchip_cycle<I + 1>(mt, s, pin);
-        // prolongation (piecewise constant) and post-smoothing
-        const float inv = mt.inv_ny[l];
-        for (int e = threadIdx.x; e < M; e += kOnchipThreads) {
-            int i, j;
-            cell_ij(e, ny, inv, i, j);
-            s.X[o + e] += s.X[co + (i >> 1) * cny + (j >> 1)];
-        }
-        __syncthreads();
-        onchip_smooth(mt, s, l, pin, 2, kW2, kW1);
+            }
+        s.B[co + e] = r;
+        s.X[co + e] = 0.0;
     }
+    __syncthreads();
 }
 
+__device__ __forceinline__ void onchip_prolong(const OnchipMeta& mt, const OnchipSmem& s, int l) {
+    const int M = mt.M[l], ny = mt.ny[l], o = mt.off[l], cny = mt.ny[l + 1], co = mt.off[l + 1];
+    const float inv = mt.inv_ny[l];
+    for (int e = threadIdx.x; e < M; e += kOnchipThreads) {
+        int i, j;
+        cell_ij(e, ny, inv, i, j);
+        s.X[o + e] += s.X[co + (i >> 1) * cny + (j >> 1)];
+    }
+    __syncthreads();
+}
+
+// One CTA per member runs the cycle on the shared-memory hierarchy.  The cycle (V, or W on the
+// levels of at least `wmin` cells) is an explicit state machine: `left` packs, 4 bits per level,
+// how many cycles are still to be run on that level; every control variable is CTA-uniform.
 __global__ void __launch_bounds__(kOnchipThreads, 1)
-k_mg_onchip(const __grid_constant__ OnchipMeta mt_in, const double* __restrict__ b_in, double* __restrict__ x_out,
+k_mg_onchip(const __grid_constant__ OnchipMeta mt, const double* __restrict__ b_in, double* __restrict__ x_out,
             const double* __restrict__ pin, const int* __restrict__ done) {
     extern __shared__ double sm[];
-    __shared__ OnchipMeta mt;  // shared copy: the recursive (non-inlined) cycle takes it by reference
     const int m = blockIdx.x;
     if (done[m]) return;
-    for (int i = threadIdx.x; i < (int)(sizeof(OnchipMeta) / sizeof(int)); i += kOnchipThreads)
-        reinterpret_cast<int*>(&mt)[i] = reinterpret_cast<const int*>(&mt_in)[i];
-    __syncthreads();
     OnchipSmem s;
     s.X = sm;
     s.B = sm + mt.total;
@@ -353,29 +357,43 @@ k_mg_onchip(const __grid_constant__ OnchipMeta mt_in, const double* __restrict__
     }
     __syncthreads();
     const double pinv = pin[m];
-    onchip_cycle<0>(mt, s, pinv);
-    if (M0 >= mt.wmin) onchip_cycle<0>(mt, s, pinv);
+    unsigned long long left = (M0 >= mt.wmin) ? 2ull : 1ull;
+    int l = 0;
+    bool descend = true;
+    while (true) {
+        if (descend) {  // start a cycle on level l
+            if (l == mt.n - 1) {
+                if (mt.M[l] == 1) {
+                    if (threadIdx.x == 0) s.X[mt.off[l]] = s.B[mt.off[l]] * s.DV[mt.off[l]];
+                    __syncthreads();
+                } else {
+                    onchip_smooth(mt, s, l, pinv, 8, kW1, kW2);
+                }
+                left -= 1ull << (4 * l);
+                descend = false;
+            } else {
+                onchip_smooth(mt, s, l, pinv, 2, kW1, kW2);
+                onchip_restrict(mt, s, l, pinv);
+                ++l;
+                left |= ((mt.M[l] >= mt.wmin) ? 2ull : 1ull) << (4 * l);
+            }
+        } else {  // a cycle on level l has just finished
+            if ((left >> (4 * l)) & 15ull) {
+                descend = true;
+            } else if (l == 0) {
+                break;
+            } else {
+                --l;
+                onchip_prolong(mt, s, l);
+                onchip_smooth(mt, s, l, pinv, 2, kW2, kW1);
+                left -= 1ull << (4 * l);
+            }
+        }
+    }
     for (int e = threadIdx.x; e < M0; e += kOnchipThreads) x_out[(int64_t)m * M0 + e] = s.X[e];
 }
 
 // ---- CG kernels -------------------------------------------------------------------------------
-// y = A x on one cell of level 0, x taken from the shared tile (li = local index incl. halo row)
-__device__ __forceinline__ double apply_A(const Geo& g, const double* xs, int li, int row, int col, int c,
-                                          const double* __restrict__ TXl, const double* __restrict__ TYl,
-                                          double pin) {
-    const double xc = xs[li];
-    const double txl = TXl[c];
-    const double tyl = TYl[c];
-    const double txh = row < g.Nx - 1 ? TXl[c + g.Ny] : 0.0;
-    const double tyh = col < g.Ny - 1 ? TYl[c + 1] : 0.0;
-    double y = txl * (xc - xs[li - g.Ny]);
-    y = fma(txh, xc - xs[li + g.Ny], y);
-    if (col > 0) y = fma(tyl, xc - xs[li - 1], y);
-    if (col < g.Ny - 1) y = fma(tyh, xc - xs[li + 1], y);
-    if (c == 0) y = fma(pin, xc, y);
-    return y;
-}
-
 // r = q - A x0 (warm start), optional Jacobi z = r/diag; partial (r,z), (r,r); ||q||^2
 template <bool JACOBI>
 __global__ void __launch_bounds__(kThreads)
@@ -392,9 +410,12 @@ k_cg_init(Geo g, Wells w, int step, double* __restrict__ X, const double* __rest
     const int r0 = t * g.R, r1 = min(r0 + g.R, g.Nx), rows = r1 - r0;
     const int64_t off = (int64_t)m * g.M;
     load_wells(w, m, step, wc, wr);
-    for (int i = threadIdx.x; i < (rows + 2) * g.Ny; i += blockDim.x) {
-        const int row = r0 - 1 + i / g.Ny;
-        sm[i] = (row >= 0 && row < g.Nx) ? X[off + (int64_t)row * g.Ny + i % g.Ny] : 0.0;
+    const int ny = g.Ny, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nW = kThreads >> 5;
+    for (int lr = warp; lr < rows + 2; lr += nW) {
+        const int row = r0 - 1 + lr;
+        const bool in = row >= 0 && row < g.Nx;
+        const double* xr = X + off + (int64_t)row * ny;
+        for (int col = lane; col < ny; col += 32) sm[lr * ny + col] = in ? xr[col] : 0.0;
     }
     __syncthreads();
     double q2 = 0.0;  // ||q||^2 with coincident wells merged
@@ -414,22 +435,25 @@ k_cg_init(Geo g, Wells w, int step, double* __restrict__ X, const double* __rest
     __syncthreads();
     const double pinv = pin[m];
     double rz = 0.0, rr = 0.0;
-    for (int i = threadIdx.x; i < rows * g.Ny; i += blockDim.x) {
-        const int li = i + g.Ny;
-        const int row = r0 + i / g.Ny, col = i % g.Ny, c = row * g.Ny + col;
-        double r = 0.0;
-        if (q2 == 0.0) {  // no sources: the pinned system has the zero solution
-            X[off + c] = 0.0;
-        } else {
-            r = cell_source(c, w.n, wc, wr) - apply_A(g, sm, li, row, col, c, TXl + off, TYl + off, pinv);
+    for (int lr = warp; lr < rows; lr += nW) {
+        const int c0 = (r0 + lr) * ny;
+        const double* xr = sm + (lr + 1) * ny;
+        for (int col = lane; col < ny; col += 32) {
+            const int c = c0 + col;
+            double r = 0.0;
+            if (q2 == 0.0) {  // no sources: the pinned system has the zero solution
+                X[off + c] = 0.0;
+            } else {
+                r = cell_source(c, w.n, wc, wr) - stencil(xr, col, ny, TXl + off + c, TYl + off + c, c == 0, pinv);
+            }
+            Rv[off + c] = r;
+            if (JACOBI) {
+                const double z = r * dinv[off + c];
+                Z[off + c] = z;
+                rz = fma(r, z, rz);
+            }
+            rr = fma(r, r, rr);
         }
-        Rv[off + c] = r;
-        if (JACOBI) {
-            const double z = r * dinv[off + c];
-            Z[off + c] = z;
-            rz = fma(r, z, rz);
-        }
-        rr = fma(r, r, rr);
     }
     if (JACOBI) rz = block_sum(rz, red);
     rr = block_sum(rr, red);
@@ -482,25 +506,32 @@ k_cg_spmv(Geo g, int k, const double* __restrict__ Z, const double* __restrict__
     }
     const int r0 = t * g.R, r1 = min(r0 + g.R, g.Nx), rows = r1 - r0;
     const int64_t off = (int64_t)m * g.M;
-    for (int i = threadIdx.x; i < (rows + 2) * g.Ny; i += blockDim.x) {
-        const int row = r0 - 1 + i / g.Ny;
-        double pn = 0.0;
-        if (row >= 0 && row < g.Nx) {
-            const int64_t c = off + (int64_t)row * g.Ny + i % g.Ny;
-            pn = (k > 0) ? fma(beta, Pin[c], Z[c]) : Z[c];
-            if (row >= r0 && row < r1) Pout[c] = pn;
+    const int ny = g.Ny, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nW = kThreads >> 5;
+    for (int lr = warp; lr < rows + 2; lr += nW) {
+        const int row = r0 - 1 + lr;
+        const bool in = row >= 0 && row < g.Nx, own = row >= r0 && row < r1;
+        const int64_t c0 = off + (int64_t)row * ny;
+        for (int col = lane; col < ny; col += 32) {
+            double pn = 0.0;
+            if (in) {
+                pn = (k > 0) ? fma(beta, Pin[c0 + col], Z[c0 + col]) : Z[c0 + col];
+                if (own) Pout[c0 + col] = pn;
+            }
+            sm[lr * ny + col] = pn;
         }
-        sm[i] = pn;
     }
     __syncthreads();
     const double pinv = pin[m];
     double pAp = 0.0;
-    for (int i = threadIdx.x; i < rows * g.Ny; i += blockDim.x) {
-        const int li = i + g.Ny;
-        const int row = r0 + i / g.Ny, col = i % g.Ny, c = row * g.Ny + col;
-        const double ap = apply_A(g, sm, li, row, col, c, TXl + off, TYl + off, pinv);
-        AP[off + c] = ap;
-        pAp = fma(sm[li], ap, pAp);
+    for (int lr = warp; lr < rows; lr += nW) {
+        const int c0 = (r0 + lr) * ny;
+        const double* xr = sm + (lr + 1) * ny;
+        for (int col = lane; col < ny; col += 32) {
+            const int c = c0 + col;
+            const double ap = stencil(xr, col, ny, TXl + off + c, TYl + off + c, c == 0, pinv);
+            AP[off + c] = ap;
+            pAp = fma(xr[col], ap, pAp);
+        }
     }
     pAp = block_sum(pAp, red);
     if (threadIdx.x == 0) part_pAp[(int64_t)m * g.nTiles + t] = pAp;
@@ -615,9 +646,11 @@ int pressure_solve(hm_ctx* ctx, const Geo& g, const Wells& w, int step, int nm, 
             const size_t n = (size_t)nm * lv[l].M;
             double *tx, *ty, *dv, *bq;
             snprintf(name, sizeof name, "mg.TX%d", l);
-            HM_CHECK(ctx->ws.get(name, n, &tx));
+            HM_CHECK(ctx->ws.get(name, n + (size_t)lv[l].ny, &tx));  // + zero pads, see stencil()
             snprintf(name, sizeof name, "mg.TY%d", l);
-            HM_CHECK(ctx->ws.get(name, n, &ty));
+            HM_CHECK(ctx->ws.get(name, n + 1, &ty));
+            HM_CUDA(cudaMemsetAsync(tx + n, 0, (size_t)lv[l].ny * sizeof(double), st));
+            HM_CUDA(cudaMemsetAsync(ty + n, 0, sizeof(double), st));
             snprintf(name, sizeof name, "mg.dv%d", l);
             HM_CHECK(ctx->ws.get(name, n, &dv));
             lv[l].TX = tx;

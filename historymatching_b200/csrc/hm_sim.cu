@@ -19,6 +19,8 @@
 //   k_cg_update    read x,r,p,Ap,dinv  write x,r,z               64 B / iteration
 //   k_flux_cfl     read P,TXl,TYl      write Vxl,Vyl             40 B / solve
 //   k_sat_substep  read S,Vxl,Vyl      write S'                  32 B / sub-step
+#include <cooperative_groups.h>
+
 #include "hm_sim_common.cuh"
 
 using namespace hmsim;
@@ -148,7 +150,9 @@ struct Fluid {
 // a / b for b well inside the float range: float reciprocal seed, two Newton steps and one
 // residual correction (no special-case branches; agrees with IEEE division to <= 1 ulp).
 __device__ __forceinline__ double fast_div(double a, double b) {
-    double r = (double)__frcp_rn((float)b);
+    float r32;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r32) : "f"((float)b));  // one MUFU.RCP, ~2^-23
+    double r = (double)r32;
     r = r * fma(-b, r, 2.0);
     r = r * fma(-b, r, 2.0);
     const double q = a * r;
@@ -262,6 +266,197 @@ k_sat_substep(Geo g, Fluid fl, Wells w, int step, int it, double dt, const int* 
     }
 }
 
+// ---- K4b: the whole sub-step loop of one time step in ONE launch (thread-block clusters) ------------
+// The face fluxes are frozen during the Nts sub-steps of a time step.  The tiles of one member form
+// a thread-block cluster (nTiles <= 16 CTAs); every CTA keeps the saturation and the five upwind
+// stencil coefficients of its cells in REGISTERS for all Nts sub-steps, publishes fw(S) of its rows
+// in its own shared memory and pushes its first / last row into the neighbouring CTAs' halo rows
+// through distributed shared memory.  One cluster barrier per sub-step (the fw tiles are double
+// buffered).  HBM is touched once per time step (S in, fluxes in, S out) instead of once per
+// sub-step, and the per-sub-step FP64 work drops from ~42 to ~20 operations per cell because the
+// coefficients are not rebuilt.
+// Halo exchange between the CTAs of a cluster without cluster-scope fences: the sender writes each
+// value with st.async (a remote shared-memory store that performs complete_tx on an mbarrier of
+// the RECEIVING CTA); the receiver posts the expected byte count on that mbarrier and waits on its
+// phase.  (A cluster barrier per sub-step costs a GPU-scope MEMBAR plus an L1 invalidate, CCTL.IVALL,
+// on this architecture and dominated the sub-step.)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, int cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, int parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "l"(__double_as_longlong(v)), "r"(remote_bar) : "memory");
+}
+
+template <bool HAS_POR, int NT>
+__global__ void __launch_bounds__(NT, 1)
+k_sat_cluster(Geo g, Fluid fl, Wells w, int step, double dt, const int* __restrict__ nts,
+              const double* __restrict__ Sin, double* __restrict__ Sout, const double* __restrict__ Vxl,
+              const double* __restrict__ Vyl, const double* __restrict__ por) {
+    namespace cg = cooperative_groups;
+    extern __shared__ double smc[];  // fw[2][(R+2)*Ny] (halo row, R tile rows, halo row), src[R*Ny]
+    __shared__ int wc[kMaxWells];
+    __shared__ double wr[kMaxWells];
+    constexpr int CPT = kTileCells / NT;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int m = blockIdx.x / g.nTiles, t = blockIdx.x % g.nTiles;  // t == rank in the cluster
+    const int r0 = t * g.R, r1 = min(r0 + g.R, g.Nx), rows = r1 - r0;
+    const int Ny = g.Ny, nInt = rows * Ny, fwLen = (g.R + 2) * Ny;
+    const int64_t base = (int64_t)m * g.M + (int64_t)r0 * Ny;
+    const int n = nts[m];
+    double* const fwb0 = smc;
+    double* const fwb1 = smc + fwLen;
+    double* srcs = smc + 2 * fwLen;
+    load_wells(w, m, step, wc, wr);
+    for (int e = threadIdx.x; e < 2 * fwLen; e += NT) smc[e] = 0.0;  // halo rows of boundary tiles stay zero
+    for (int e = threadIdx.x; e < nInt; e += NT) srcs[e] = 0.0;
+    __syncthreads();
+    const double dts = n > 0 ? dt / (double)n : 0.0;
+    const double dtx0 = dts / g.h2;
+    for (int i = threadIdx.x; i < w.n; i += NT) {  // wells of this tile: signed source * dtx
+        const int c = wc[i], e = c - r0 * Ny;
+        if (e < 0 || e >= nInt) continue;
+        bool first = true;
+        for (int k = 0; k < i; ++k) first = first && (wc[k] != c);
+        if (!first) continue;
+        double dtx = dtx0;
+        if (HAS_POR) dtx = dts / (g.h2 * por[c]);
+        srcs[e] = cell_source(c, w.n, wc, wr) * dtx;
+    }
+    __syncthreads();
+
+    double s[CPT], aW[CPT], aS[CPT], aN[CPT], aE[CPT], dg[CPT], sr[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+        const int e = threadIdx.x + j * NT;
+        s[j] = aW[j] = aS[j] = aN[j] = aE[j] = dg[j] = sr[j] = 0.0;
+        if (e < nInt) {
+            const int64_t gc = base + e;
+            s[j] = Sin[gc];
+            const double vxl = Vxl[gc], vyl = Vyl[gc], vxh = Vxl[gc + Ny], vyh = Vyl[gc + 1];
+            double hdt = 0.5 * dtx0;
+            if (HAS_POR) hdt = 0.5 * (dts / (g.h2 * por[(int64_t)r0 * Ny + e]));
+            // max(v,0) = (v+|v|)/2, min(v,0) = (v-|v|)/2 (exact)
+            aW[j] = hdt * (vxl + fabs(vxl));
+            aS[j] = hdt * (vyl + fabs(vyl));
+            aN[j] = hdt * (fabs(vyh) - vyh);
+            aE[j] = hdt * (fabs(vxh) - vxh);
+            const double q = srcs[e];
+            dg[j] = hdt * (((vyl - vyh) + (vxl - vxh)) - ((fabs(vyl) + fabs(vyh)) + (fabs(vxl) + fabs(vxh)))) +
+                    fmin(q, 0.0);
+            sr[j] = fmax(q, 0.0);
+        }
+    }
+    // remote halo rows: my first row is the high halo of tile t-1, my last row the low halo of tile t+1
+    __shared__ __align__(8) unsigned long long bars[2];
+    const uint32_t bar0 = smem_u32(&bars[0]), bar1 = smem_u32(&bars[1]);
+    const bool hasUp = t > 0, hasDn = t < g.nTiles - 1;
+    const int nNbr = (hasUp ? 1 : 0) + (hasDn ? 1 : 0);
+    if (threadIdx.x == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // shared::cluster addresses of the neighbours' halo rows and barriers, per buffer parity
+    uint32_t up0 = 0, up1 = 0, dn0 = 0, dn1 = 0, upb0 = 0, upb1 = 0, dnb0 = 0, dnb1 = 0;
+    if (hasUp) {
+        up0 = map_to_cta(smem_u32(fwb0 + (g.R + 1) * Ny), t - 1);
+        up1 = map_to_cta(smem_u32(fwb1 + (g.R + 1) * Ny), t - 1);
+        upb0 = map_to_cta(bar0, t - 1);
+        upb1 = map_to_cta(bar1, t - 1);
+    }
+    if (hasDn) {
+        dn0 = map_to_cta(smem_u32(fwb0), t + 1);
+        dn1 = map_to_cta(smem_u32(fwb1), t + 1);
+        dnb0 = map_to_cta(bar0, t + 1);
+        dnb1 = map_to_cta(bar1, t + 1);
+    }
+    // Only the first and last row of a tile depend on the neighbours' data.  Per sub-step: publish fw
+    // (own tile, and the two edge rows into the neighbours' halo rows), update the inner rows after a
+    // CTA-local barrier, wait for the neighbours' rows, update the two edge rows.
+    bool edge[CPT], sendUp[CPT], sendDn[CPT];
+    bool anyEdge = false;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+        const int e = threadIdx.x + j * NT;
+        const bool in = e < nInt;
+        edge[j] = in && (e < Ny || e >= nInt - Ny);
+        sendUp[j] = in && e < Ny && hasUp;
+        sendDn[j] = in && e >= nInt - Ny && hasDn;
+        anyEdge = anyEdge || edge[j];
+    }
+    const bool full = nInt == kTileCells;
+    cluster.sync();  // tiles zeroed and mbarriers initialised in every CTA before remote traffic starts
+    for (int sub = 0; sub < n; ++sub) {
+        const bool odd = sub & 1;
+        double* fw = (odd ? fwb1 : fwb0) + Ny + threadIdx.x;
+        const uint32_t up = (odd ? up1 : up0) + 8u * threadIdx.x, upb = odd ? upb1 : upb0;
+        const uint32_t dn = (odd ? dn1 : dn0) + 8u * (threadIdx.x - (nInt - Ny)), dnb = odd ? dnb1 : dnb0;
+        const uint32_t mybar = odd ? bar1 : bar0;
+        if (threadIdx.x == 0 && nNbr) mbar_expect_tx(mybar, nNbr * Ny * 8);
+        double f[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            f[j] = frac_flow_fast(s[j], fl);
+            if (full || threadIdx.x + j * NT < nInt) fw[j * NT] = f[j];
+            if (sendUp[j]) st_async_f64(up + 8u * (j * NT), f[j], upb);
+            if (sendDn[j]) st_async_f64(dn + 8u * (j * NT), f[j], dnb);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            if ((full || threadIdx.x + j * NT < nInt) && !edge[j]) {
+                const double* fp = fw + j * NT;
+                double acc = aW[j] * fp[-Ny];
+                acc = fma(aS[j], fp[-1], acc);
+                acc = fma(dg[j], f[j], acc);
+                acc = fma(aN[j], fp[1], acc);
+                acc = fma(aE[j], fp[Ny], acc);
+                s[j] += acc + sr[j];
+            }
+        }
+        if (anyEdge) {
+            if (nNbr) mbar_wait(mybar, (sub >> 1) & 1);
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                if (edge[j]) {
+                    const double* fp = fw + j * NT;
+                    double acc = aW[j] * fp[-Ny];
+                    acc = fma(aS[j], fp[-1], acc);
+                    acc = fma(dg[j], f[j], acc);
+                    acc = fma(aN[j], fp[1], acc);
+                    acc = fma(aE[j], fp[Ny], acc);
+                    s[j] += acc + sr[j];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+        const int e = threadIdx.x + j * NT;
+        if (e < nInt) Sout[base + e] = s[j];
+    }
+    cluster.sync();  // no CTA may exit while a neighbour can still write into its shared memory
+}
+
 // ---- obs gather / history / status ------------------------------------------------------------
 __global__ void k_gather_obs(int n_members, int M, int n_obs, const int32_t* __restrict__ obs_cell,
                              const double* __restrict__ S, double* __restrict__ obs, int n_steps,
@@ -357,8 +552,8 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
     double *TXl, *TYl, *dinv, *P, *Vxl, *Vyl, *Sa, *Sb;
     double *part_pm, *pin;
     int *done, *iters, *nts, *cg_fail, *counters;
-    HM_CHECK(ctx->ws.get("sim.TXl", vec, &TXl));
-    HM_CHECK(ctx->ws.get("sim.TYl", vec, &TYl));
+    HM_CHECK(ctx->ws.get("sim.TXl", vec + (size_t)d.Ny, &TXl));  // + zero pads: high faces read unguarded
+    HM_CHECK(ctx->ws.get("sim.TYl", vec + 1, &TYl));
     HM_CHECK(ctx->ws.get("sim.dinv", vec, &dinv));
     HM_CHECK(ctx->ws.get("sim.P", vec, &P));
     HM_CHECK(ctx->ws.get("sim.Vxl", vec + (size_t)d.Ny, &Vxl));  // + zero pad, see sat_tile_body
@@ -402,11 +597,23 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
         HM_CUDA(cudaFuncSetAttribute(k_sat_substep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     }
     const int copy_blocks = (int)((vec + 255) / 256);
+    // transport: all sub-steps of a time step in one cluster launch when the member's tiles fit a cluster
+    const bool use_cluster = d.sat_block != 1 && g.nTiles <= 16;
+    const size_t smem_cluster = ((size_t)2 * (g.R + 2) * d.Ny + (size_t)g.R * d.Ny) * sizeof(double);
+    const int cluster_threads = d.sat_block == 2 ? 512 : 1024;
+    if (use_cluster) {
+        auto kern = d.por ? (cluster_threads == 1024 ? k_sat_cluster<true, 1024> : k_sat_cluster<true, 512>)
+                          : (cluster_threads == 1024 ? k_sat_cluster<false, 1024> : k_sat_cluster<false, 512>);
+        HM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cluster));
+        if (g.nTiles > 8) HM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    }
 
     // initial state: S <- S0, P <- 0 (cold start of the first solve), flags
     k_copy_rows<<<copy_blocks, 256, 0, st>>>(nm, (int)M, d.S0 + (int64_t)m0 * d.S0_member_stride,
                                               d.S0_member_stride, Sa, M);
     HM_CUDA(cudaMemsetAsync(P, 0, vec * sizeof(double), st));
+    HM_CUDA(cudaMemsetAsync(TXl + vec, 0, (size_t)d.Ny * sizeof(double), st));
+    HM_CUDA(cudaMemsetAsync(TYl + vec, 0, sizeof(double), st));
     HM_CUDA(cudaMemsetAsync(Vxl + vec, 0, (size_t)d.Ny * sizeof(double), st));
     HM_CUDA(cudaMemsetAsync(Vyl + vec, 0, sizeof(double), st));
     HM_CUDA(cudaMemsetAsync(cg_fail, 0, nm * sizeof(int), st));
@@ -441,18 +648,41 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
         ctx->sim_stats.kernel_launches += 2;
 
         timer.mark(3);
-        for (int it = 0; it < max_nts; ++it) {
-            if (d.por)
-                k_sat_substep<true><<<grid, kThreads, smem1, st>>>(g, fl, w, step, it, d.dt, nts, Scur, Snxt,
-                                                                    Vxl, Vyl, d.por);
-            else
-                k_sat_substep<false><<<grid, kThreads, smem1, st>>>(g, fl, w, step, it, d.dt, nts, Scur, Snxt,
-                                                                     Vxl, Vyl, nullptr);
+        int sat_launches = 0;
+        if (use_cluster) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)grid);
+            cfg.blockDim = dim3(cluster_threads);
+            cfg.dynamicSmemBytes = smem_cluster;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)g.nTiles;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            const double* porp = d.por;
+            auto kern = d.por ? (cluster_threads == 1024 ? k_sat_cluster<true, 1024> : k_sat_cluster<true, 512>)
+                              : (cluster_threads == 1024 ? k_sat_cluster<false, 1024> : k_sat_cluster<false, 512>);
+            HM_CUDA(cudaLaunchKernelEx(&cfg, kern, g, fl, w, step, d.dt, (const int*)nts, (const double*)Scur, Snxt,
+                                       (const double*)Vxl, (const double*)Vyl, porp));
             std::swap(Scur, Snxt);
+            sat_launches = 1;
+        } else {
+            for (int it = 0; it < max_nts; ++it, ++sat_launches) {
+                if (d.por)
+                    k_sat_substep<true><<<grid, kThreads, smem1, st>>>(g, fl, w, step, it, d.dt, nts, Scur, Snxt,
+                                                                        Vxl, Vyl, d.por);
+                else
+                    k_sat_substep<false><<<grid, kThreads, smem1, st>>>(g, fl, w, step, it, d.dt, nts, Scur, Snxt,
+                                                                         Vxl, Vyl, nullptr);
+                std::swap(Scur, Snxt);
+            }
         }
         ctx->sim_stats.sat_substeps += max_nts;
-        ctx->sim_stats.kernel_launches += max_nts;
-        ctx->sim_stats.sat_kernel_launches += max_nts;
+        ctx->sim_stats.kernel_launches += sat_launches;
+        ctx->sim_stats.sat_kernel_launches += sat_launches;
 
         timer.mark(4);
         if (obs && d.n_obs > 0) {
