@@ -77,6 +77,9 @@ SYMBOLS = {
     "hm_center": (C.c_int, [C.c_void_p, i64, i64, C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, C.c_int]),
     "hm_ies_step": (C.c_int, [C.c_void_p, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_double]),
+    "hm_iles_step": (C.c_int, [C.c_void_p, i64, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_double]),
+    "hm_iles_recompose": (C.c_int, [C.c_void_p, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

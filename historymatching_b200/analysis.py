@@ -162,6 +162,45 @@ def IES(prior_ens, obs_ens, obs, perturbs, decorr, xStep=1.0, iMax=4):
     return _back(_recompose(ctx, x0, W, X0), was_np), stats
 
 
+def ILES(prior_ens, obs_ens, obs, perturbs, decorr, taper, xStep=1.0, iMax=4):
+    """Localised iterative ensemble smoother; see ``HistoryMatch.py:1007-1064``.
+
+    One ``N x N`` weight matrix per parameter (``M N^2`` doubles on the device); every
+    iteration re-runs ``obs_ens`` and applies the tapered Gauss-Newton step of all
+    parameters in one batched kernel (``hm_iles_step``).
+    """
+    torch = _torch()
+    was_np = not _is_tensor(prior_ens)
+    stats = Stats(E=[], Eo=[])
+    E0 = _dev(prior_ens)
+    y, pert, dec, tap = _dev(obs), _dev(perturbs), _dev(decorr), _dev(taper)
+    N, M = E0.shape
+    p = y.shape[0]
+    assert tap.shape == (M, p)
+    ctx = _ctx(E0)
+    X0 = torch.empty_like(E0)
+    x0 = torch.empty(M, dtype=torch.float64, device=E0.device)
+    _lib.check(ctx.lib.hm_center(ctx.handle, N, M, _p(E0), M, _p(X0), M, _p(x0), 0))
+    Ws = torch.eye(N, dtype=torch.float64, device=E0.device).repeat(M, 1, 1).contiguous()
+
+    def recompose():
+        E = torch.empty_like(E0)
+        _lib.check(ctx.lib.hm_iles_recompose(ctx.handle, N, M, _p(Ws), _p(X0), _p(x0), _p(E)))
+        return E
+
+    for _ in range(iMax):
+        E = recompose()
+        Eo = obs_ens(_back(E, was_np))
+        stats.E.append(_back(E, was_np))
+        stats.Eo.append(Eo)
+        Eo_d = _dev(Eo)
+        assert Eo_d.shape == (N, p)
+        ctx.use_torch_stream()
+        _lib.check(ctx.lib.hm_iles_step(ctx.handle, N, M, p, _p(Ws), _p(Eo_d), _p(y), _p(pert), _p(dec), _p(tap),
+                                        float(xStep)))
+    return _back(recompose(), was_np), stats
+
+
 def es_mda(prior_ens, obs_ens, obs, R12, alphas, decorr=None, perturbs=None):
     """ES-MDA: ``len(alphas)`` forward runs + ES updates with inflated obs-error
     covariance ``alpha_i R`` (``sum 1/alpha_i == 1``).  Not in the reference; defined on

@@ -193,6 +193,189 @@ k_local_analysis(int64_t M, int p, double nm1, const double* __restrict__ A,
     if (tid == 0 && s_fail) atomicExch(fail, 1);
 }
 
+// ---- batched localised IES step (HistoryMatch.py:1034-1059) -------------------------------------
+// One CTA per parameter i with its own N x N weight matrix Wi.  Everything is in shared memory:
+//   Ai = Wi^-1 (in-place Gauss-Jordan with partial pivoting; the reference uses pinv of the square,
+//   non-singular Wi), Y0 = center(Ai) Si, G = Di Y0^T + (N-1)(I - Wi), C = Y0 Y0^T + (N-1) I
+//   (= the inverse of the reference's SVD expression for covw), Cholesky of C, dW = G C^-1,
+//   Wi += xStep dW.  Si / Di are the tapered, active columns of S / D as in k_local_analysis.
+__global__ void __launch_bounds__(256)
+k_iles_step(int N, int p, double xStep, const double* __restrict__ S, const double* __restrict__ D,
+            const double* __restrict__ taper, double* __restrict__ Ws, int* __restrict__ fail) {
+    extern __shared__ double sm[];
+    const int64_t ip = blockIdx.x;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double* A = sm;                 // N*N  : Wi -> Wi^-1 -> centred
+    double* G = A + N * N;          // N*N
+    double* Cc = G + N * N;         // N*N
+    double* Y0 = Cc + N * N;        // N*p (only the first n columns used, row pitch n)
+    double* c = Y0 + (size_t)N * p; // p
+    double* colmean = c + p;        // N
+    int* idx = (int*)(colmean + N); // p
+    int* ipiv = idx + p;            // N
+    __shared__ int s_n, s_piv, s_fail;
+    double* W = Ws + ip * N * N;
+    const double nm1 = (double)(N - 1);
+
+    if (tid == 0) {
+        int n = 0;
+        for (int j = 0; j < p; ++j) {
+            const double cj = sqrt(taper[ip * p + j]);
+            if (cj > 1e-2) {
+                idx[n] = j;
+                c[n] = cj;
+                ++n;
+            }
+        }
+        s_n = n;
+        s_fail = 0;
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n == 0) return;  // no active observation: dW = 0 (HistoryMatch.py:1039-1040)
+    for (int e = tid; e < N * N; e += nt) A[e] = W[e];
+    __syncthreads();
+    // in-place Gauss-Jordan inversion with partial pivoting
+    for (int k = 0; k < N; ++k) {
+        if (tid < 32) {
+            double best = -1.0;
+            int bi = k;
+            for (int i = k + tid; i < N; i += 32) {
+                const double v = fabs(A[i * N + k]);
+                if (v > best) {
+                    best = v;
+                    bi = i;
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) {
+                    best = ob;
+                    bi = oi;
+                }
+            }
+            if (tid == 0) {
+                s_piv = bi;
+                ipiv[k] = bi;
+                if (!(best > 0.0)) s_fail = 1;
+            }
+        }
+        __syncthreads();
+        const int pv = s_piv;
+        if (pv != k)
+            for (int j = tid; j < N; j += nt) {
+                const double t0 = A[k * N + j];
+                A[k * N + j] = A[pv * N + j];
+                A[pv * N + j] = t0;
+            }
+        __syncthreads();
+        const double dinv = 1.0 / A[k * N + k];
+        __syncthreads();
+        for (int j = tid; j < N; j += nt) A[k * N + j] = (j == k) ? dinv : A[k * N + j] * dinv;
+        __syncthreads();
+        for (int e = tid; e < N * N; e += nt) {
+            const int i = e / N, j = e % N;
+            if (i == k) continue;
+            const double f = A[i * N + k];
+            // column k of the other rows becomes -f * dinv, the rest is eliminated
+            if (j == k) Cc[i] = f;  // stash the multipliers: they are overwritten below
+        }
+        __syncthreads();
+        for (int e = tid; e < N * N; e += nt) {
+            const int i = e / N, j = e % N;
+            if (i == k) continue;
+            const double f = Cc[i];
+            A[i * N + j] = (j == k) ? -f * dinv : A[i * N + j] - f * A[k * N + j];
+        }
+        __syncthreads();
+    }
+    for (int k = N - 1; k >= 0; --k) {  // undo the row swaps as column swaps
+        const int pv = ipiv[k];
+        if (pv != k)
+            for (int i = tid; i < N; i += nt) {
+                const double t0 = A[i * N + k];
+                A[i * N + k] = A[i * N + pv];
+                A[i * N + pv] = t0;
+            }
+        __syncthreads();
+    }
+    // centre the columns of Wi^-1 (axis 0)
+    for (int j = tid; j < N; j += nt) {
+        double sacc = 0.0;
+        for (int i = 0; i < N; ++i) sacc += A[i * N + j];
+        colmean[j] = sacc / (double)N;
+    }
+    __syncthreads();
+    for (int e = tid; e < N * N; e += nt) A[e] -= colmean[e % N];
+    __syncthreads();
+    // Y0 = A Si,  Si[k][a] = S[k][idx[a]] c[a]
+    for (int e = tid; e < N * n; e += nt) {
+        const int r = e / n, a = e % n;
+        double acc = 0.0;
+        for (int k = 0; k < N; ++k) acc = fma(A[r * N + k], S[(int64_t)k * p + idx[a]], acc);
+        Y0[r * n + a] = acc * c[a];
+    }
+    __syncthreads();
+    // G = Di Y0^T + (N-1)(I - Wi) ;  C = Y0 Y0^T + (N-1) I
+    for (int e = tid; e < N * N; e += nt) {
+        const int r = e / N, l = e % N;
+        double g = 0.0, cc = 0.0;
+        for (int a = 0; a < n; ++a) {
+            const double y = Y0[l * n + a];
+            g = fma(D[(int64_t)r * p + idx[a]] * c[a], y, g);
+            cc = fma(Y0[r * n + a], y, cc);
+        }
+        G[e] = g + nm1 * ((r == l ? 1.0 : 0.0) - W[e]);
+        Cc[e] = cc + (r == l ? nm1 : 0.0);
+    }
+    __syncthreads();
+    // Cholesky of C (lower, in place)
+    for (int k = 0; k < N; ++k) {
+        const double dkk = Cc[k * N + k];
+        if (tid == 0 && !(dkk > 0.0)) s_fail = 1;
+        const double d = sqrt(dkk);
+        __syncthreads();
+        for (int a = k + tid; a < N; a += nt) Cc[a * N + k] = (a == k) ? d : Cc[a * N + k] / d;
+        __syncthreads();
+        const int rem = N - k - 1;
+        for (int e = tid; e < rem * rem; e += nt) {
+            const int a = k + 1 + e / rem, b = k + 1 + e % rem;
+            if (b <= a) Cc[a * N + b] -= Cc[a * N + k] * Cc[b * N + k];
+        }
+        __syncthreads();
+    }
+    // dW rows: solve C x = G[r,:]^T, one row per thread
+    for (int r = tid; r < N; r += nt) {
+        double* g = G + r * N;
+        for (int k = 0; k < N; ++k) {
+            double v = g[k];
+            for (int a = 0; a < k; ++a) v -= Cc[k * N + a] * g[a];
+            g[k] = v / Cc[k * N + k];
+        }
+        for (int k = N - 1; k >= 0; --k) {
+            double v = g[k];
+            for (int a = k + 1; a < N; ++a) v -= Cc[a * N + k] * g[a];
+            g[k] = v / Cc[k * N + k];
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < N * N; e += nt) W[e] = fma(xStep, G[e], W[e]);
+    if (tid == 0 && s_fail) atomicExch(fail, 1);
+}
+
+// E[:, i] = x0[i] + Ws[i] X0[:, i]   (recompose, HistoryMatch.py:1020-1021)
+__global__ void k_iles_recompose(int N, int64_t M, const double* __restrict__ Ws, const double* __restrict__ X0,
+                                 const double* __restrict__ x0, double* __restrict__ E) {
+    const int64_t i = blockIdx.x;
+    const double* W = Ws + i * N * N;
+    for (int r = threadIdx.x; r < N; r += blockDim.x) {
+        double acc = 0.0;
+        for (int k = 0; k < N; ++k) acc = fma(W[r * N + k], X0[(int64_t)k * M + i], acc);
+        E[(int64_t)r * M + i] = x0[i] + acc;
+    }
+}
+
 // S = center(Eo) decorr, D = (obs - Eo - perturbs) decorr (HistoryMatch.py:580-584)
 int whiten(hm_ctx* ctx, int64_t N, int64_t p, const double* Eo, const double* obs,
            const double* perturbs, const double* decorr, double** S_out, double** D_out) {
@@ -399,6 +582,36 @@ extern "C" int hm_ies_step(hm_ctx* ctx, int64_t N, int64_t p, double* W, const d
     HM_CHECK(chol_solve_right(ctx, (int)N, Cw, (int)N, G));
     k_axpy<<<(unsigned)((N * N + 255) / 256), 256, 0, st>>>(N * N, xStep, G, W);
     ctx->launches += 5;  // set_identity, ies_resid, ies_grad_b, add_diag, axpy
+    HM_CUDA(cudaGetLastError());
+    return HM_OK;
+}
+
+extern "C" int hm_iles_step(hm_ctx* ctx, int64_t N, int64_t M, int64_t p, double* Ws, const double* Eo,
+                            const double* obs, const double* perturbs, const double* decorr,
+                            const double* taper, double xStep) {
+    HM_REQUIRE(ctx && Ws && Eo && obs && perturbs && decorr && taper, "null pointer");
+    HM_REQUIRE(N > 1 && M > 0 && p > 0, "shape");
+    HM_CUDA(cudaSetDevice(ctx->device));
+    const size_t smem = ((size_t)3 * N * N + (size_t)N * p + p + N) * sizeof(double) + (size_t)(p + N) * sizeof(int);
+    HM_REQUIRE(smem <= 227 * 1024, "N, p too large for the shared-memory localised IES step (3 N^2 + N p doubles)");
+    double *S, *D;
+    int* fail;
+    HM_CHECK(whiten(ctx, N, p, Eo, obs, perturbs, decorr, &S, &D));
+    HM_CHECK(ctx->ws.get("an.info", (size_t)4, &fail));
+    HM_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), ctx->stream));
+    HM_CUDA(cudaFuncSetAttribute(k_iles_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_iles_step<<<(unsigned)M, 256, smem, ctx->stream>>>((int)N, (int)p, xStep, S, D, taper, Ws, fail);
+    ctx->launches += 1;
+    HM_CUDA(cudaGetLastError());
+    return check_info(ctx, fail, "localised IES step (singular Wi or non-SPD Gauss-Newton matrix)");
+}
+
+extern "C" int hm_iles_recompose(hm_ctx* ctx, int64_t N, int64_t M, const double* Ws, const double* X0,
+                                 const double* x0, double* E) {
+    HM_REQUIRE(ctx && Ws && X0 && x0 && E, "null pointer");
+    HM_CUDA(cudaSetDevice(ctx->device));
+    k_iles_recompose<<<(unsigned)M, 64, 0, ctx->stream>>>((int)N, M, Ws, X0, x0, E);
+    ctx->launches += 1;
     HM_CUDA(cudaGetLastError());
     return HM_OK;
 }

@@ -175,6 +175,16 @@ int hm_center(hm_ctx* ctx, int64_t N, int64_t M, const double* E, int64_t ldE, d
 int hm_ies_step(hm_ctx* ctx, int64_t N, int64_t p, double* W, const double* Eo,
                 const double* obs, const double* perturbs, const double* decorr, double xStep);
 
+/* Localised iterative smoother.  Replaces the loop body of ILES (HistoryMatch.py:1031-1062):
+ * Ws holds one (N,N) weight matrix per parameter, (M,N,N) row-major, updated in place with the
+ * tapered Gauss-Newton step of every parameter; taper is (M,p). */
+int hm_iles_step(hm_ctx* ctx, int64_t N, int64_t M, int64_t p, double* Ws, const double* Eo,
+                 const double* obs, const double* perturbs, const double* decorr,
+                 const double* taper, double xStep);
+/* E[:, i] = x0[i] + Ws[i] X0[:, i]  (recompose, HistoryMatch.py:1020-1021); E, X0 are (N,M). */
+int hm_iles_recompose(hm_ctx* ctx, int64_t N, int64_t M, const double* Ws, const double* X0,
+                      const double* x0, double* E);
+
 #ifdef __cplusplus
 }
 #endif

@@ -160,3 +160,44 @@ def test_es_update_large_linear_gaussian_property():
     d1 = ha.ens_update0(E, Eo, obs + 1.0, pert, dec) - post
     d2 = ha.ens_update0(E, Eo, obs + 1.0, 0 * pert, dec) - ha.ens_update0(E, Eo, obs, 0 * pert, dec)
     assert float((d1 - d2).abs().max()) < 1e-9
+
+
+@pytest.mark.parametrize("tag", ["small", "wide"])
+def test_iles_against_reference_golden(golden, tag):
+    """ILES (HistoryMatch.py:1007-1064): batched per-parameter Gauss-Newton steps."""
+    from historymatching_b200 import analysis as ha
+
+    g = golden("updates.npz")
+    H = g[f"{tag}_H"]
+
+    def fwd(X):
+        return np.tanh(X @ H) + 0.1 * (X @ H)
+
+    E, st = ha.ILES(obs_ens=fwd, taper=g[f"{tag}_taper"], xStep=0.6, iMax=3, **_case(g, tag))
+    np.testing.assert_allclose(E, g[f"{tag}_ILES"], **TOL)
+    np.testing.assert_allclose(np.array(st.E), g[f"{tag}_ILES_E"], **TOL)
+
+
+def test_iles_notebook_self_check_and_size(golden):
+    """HistoryMatch.py:1069-1071: ILES(taper=eye) reproduces the local ES; notebook size N=40, M=400, p=160."""
+    from historymatching_b200 import analysis as ha
+
+    g = golden("gauss_gauss.npz")
+    kw = {k: g[k][:48] if k in ("prior_ens", "perturbs") else g[k] for k in ("prior_ens", "obs", "perturbs", "decorr")}
+    ref = oa.ens_update0_loc(obs_ens=kw["prior_ens"], taper=np.eye(3), **kw)
+    out, _ = ha.ILES(obs_ens=lambda x: x, taper=np.eye(3), **kw)
+    np.testing.assert_allclose(out, ref, rtol=1e-7, atol=1e-9)
+
+    kw, _, H = _hm_case(40, 400, 160, seed=2)
+    kw.pop("obs_ens")
+    rng = np.random.RandomState(1)
+    xy_prm = rng.rand(400, 2) * [2, 1]
+    xy_obs = np.tile(rng.rand(4, 2) * [2, 1], (40, 1))
+    taper = oa.bump(oa.pairwise_distances(xy_prm, xy_obs) / 1.2)
+
+    def fwd(X):
+        return np.tanh(X @ H)
+
+    E_gpu, _ = ha.ILES(obs_ens=fwd, taper=taper, xStep=0.4, iMax=2, **kw)
+    E_ref, _ = oa.ILES(obs_ens=fwd, taper=taper, xStep=0.4, iMax=2, **kw)
+    np.testing.assert_allclose(E_gpu, E_ref, **TOL)

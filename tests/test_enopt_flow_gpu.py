@@ -1,0 +1,74 @@
+"""EnOpt-style batches (Optimise.py:112-210, 428-466): every member re-configures the wells / rates
+of a deep copy of the model and runs it; the batch lands on the GPU as ONE ensemble launch with
+per-member well lists, invalid members are penalised without disturbing the rest."""
+
+import copy
+
+import numpy as np
+import pytest
+
+from oracle import ressim as orr
+
+pytestmark = pytest.mark.gpu
+
+
+def test_npv_batches_through_collector():
+    import historymatching_b200 as hmb
+
+    hmb.activate()
+    import TPFA_ResSim as simulator
+    from tools import utils
+    from tools.utils import apply
+
+    rng = np.random.RandomState(23)
+    model = simulator.ResSim(Nx=16, Ny=16, Lx=2, Ly=1, name="Base model")
+    K = 0.1 + np.exp(1.5 * rng.randn(1, 256))
+    model.K = K
+    near01 = np.array([0.12, 0.87])
+    rate0 = 1.5
+    model.inj_xy = [[model.Lx / 2, model.Ly / 2]]
+    model.prd_xy = [[x, y] for y in model.Ly * near01 for x in model.Lx * near01]
+    model.inj_rates = rate0 * np.ones((1, 1))
+    model.prd_rates = rate0 * np.ones((4, 1)) / 4
+    wsat0 = np.zeros(model.Nxy)
+    dt, nTime = 0.025, 6
+
+    def remake(model, **params):
+        model = copy.deepcopy(model)
+        for k, v in params.items():
+            setattr(model, k, v)
+        return model
+
+    def npv(model, **params):
+        try:
+            model = remake(model, **params)
+            wsats = model.sim(dt, nTime, wsat0, pbar=False)
+            s = wsats[:, model.xy2ind(*model.prd_xy.T)]
+            prd_sat = ((s[:-1] + s[1:]) / 2).T
+            oil = dt * model.actual_rates["prd"] * (1 - prd_sat)
+            value = 100 * oil.sum() - 20 * dt * model.actual_rates["inj"].sum()
+        except Exception:
+            value = 0
+        return value
+
+    def obj(xys):
+        return npv(model, inj_xy=xys)
+
+    U = np.array([[1.0, 0.5], [0.3, 0.2], [1.7, 0.9], [2.6, 0.5], [0.9, 0.1], [-0.1, 0.3]])
+    utils.nCPU = "auto"
+    batched = apply(obj, U, pbar=False)
+    utils.nCPU = 1
+    serial = apply(obj, U, pbar=False)
+    assert batched[3] == 0 and batched[5] == 0  # outside the domain: penalised, not fatal (Optimise.py:548-555)
+    np.testing.assert_allclose(batched, serial, rtol=1e-10)
+
+    # oracle for one valid member, incl. time-dependent rates (Optimise.py:745-767)
+    sched = rate0 * (0.5 + rng.rand(1, nTime))
+    m2 = remake(model, inj_xy=[0.3, 0.2], inj_rates=sched, prd_rates=np.tile(sched / 4, (4, 1)))
+    got = m2.sim(dt, nTime, wsat0, pbar=False)
+    om = orr.OracleResSim(16, 16, 2.0, 1.0)
+    om.K = model.K
+    om.inj_xy, om.prd_xy = m2.inj_xy, m2.prd_xy
+    om.inj_rates, om.prd_rates = m2.inj_rates, m2.prd_rates
+    np.testing.assert_allclose(got, om.sim(dt, nTime, wsat0), rtol=0, atol=1e-8)
+    assert m2.actual_rates["inj"].shape == (1, nTime) and m2.actual_rates["prd"].shape == (4, nTime)
