@@ -145,25 +145,25 @@ __global__ void k_substep_count(Geo g, int n_members, double dt, const double* _
 constexpr int kSatCPT = kTileCells / kThreads;
 
 struct Fluid {
-    double swc, inv_range, inv_vw, inv_vo;
+    double inv_range;  // 1 / (1 - swc - sor)
+    double swc_ir;     // swc / (1 - swc - sor)
+    double mr;         // mobility ratio vw / vo:  fw = se^2 / (se^2 + mr (1-se)^2)
 };
-// a / b for b well inside the float range: float reciprocal seed, two Newton steps and one
-// residual correction (no special-case branches; agrees with IEEE division to <= 1 ulp).
+// a / b for b well inside the float range: MUFU.RCP seed (2^-23), one Newton step (2^-46) and a
+// residual correction of the quotient; agrees with IEEE division to <= 1 ulp, no branches.
 __device__ __forceinline__ double fast_div(double a, double b) {
     float r32;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r32) : "f"((float)b));  // one MUFU.RCP, ~2^-23
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r32) : "f"((float)b));
     double r = (double)r32;
-    r = r * fma(-b, r, 2.0);
-    r = r * fma(-b, r, 2.0);
+    r = fma(r, fma(-b, r, 1.0), r);
     const double q = a * r;
     return fma(fma(-b, q, a), r, q);
 }
 __device__ __forceinline__ double frac_flow_fast(double s, const Fluid& f) {
-    const double se = (s - f.swc) * f.inv_range;
-    const double lw = se * se * f.inv_vw;
+    const double se = fma(s, f.inv_range, -f.swc_ir);
     const double t = 1.0 - se;
-    const double lo = t * t * f.inv_vo;
-    return fast_div(lw, lw + lo);  // lw + lo >= min(1/vw,1/vo)/2 > 0 for every saturation
+    const double a = se * se;
+    return fast_div(a, fma(f.mr * t, t, a));  // denominator >= min(1, mr)/2 > 0 for every saturation
 }
 
 // The flux arrays carry a zero pad (Ny resp. 1 elements) behind the last member, and the low
@@ -405,6 +405,38 @@ k_sat_cluster(Geo g, Fluid fl, Wells w, int step, double dt, const int* __restri
     }
     const bool full = nInt == kTileCells;
     cluster.sync();  // tiles zeroed and mbarriers initialised in every CTA before remote traffic starts
+    if (full && Ny <= NT && Ny % 32 == 0) {
+        // Fast path (full tile, rows are whole warps): the first row lives in cell 0 of threads [0, Ny), the
+        // last row in cell CPT-1 of threads [NT-Ny, NT); no per-cell predicates in the loop.
+        const bool sUp = hasUp && threadIdx.x < Ny, sDn = hasDn && threadIdx.x >= NT - Ny;
+        const bool needWait = sUp || sDn;
+        for (int sub = 0; sub < n; ++sub) {
+            const bool odd = sub & 1;
+            double* fw = (odd ? fwb1 : fwb0) + Ny + threadIdx.x;
+            const uint32_t mybar = odd ? bar1 : bar0;
+            if (threadIdx.x == 0 && nNbr) mbar_expect_tx(mybar, nNbr * Ny * 8);
+            double f[CPT];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                f[j] = frac_flow_fast(s[j], fl);
+                fw[j * NT] = f[j];
+            }
+            if (sUp) st_async_f64((odd ? up1 : up0) + 8u * threadIdx.x, f[0], odd ? upb1 : upb0);
+            if (sDn) st_async_f64((odd ? dn1 : dn0) + 8u * (threadIdx.x - (NT - Ny)), f[CPT - 1], odd ? dnb1 : dnb0);
+            __syncthreads();
+            if (needWait) mbar_wait(mybar, (sub >> 1) & 1);
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const double* fp = fw + j * NT;
+                double acc = aW[j] * fp[-Ny];
+                acc = fma(aS[j], fp[-1], acc);
+                acc = fma(dg[j], f[j], acc);
+                acc = fma(aN[j], fp[1], acc);
+                acc = fma(aE[j], fp[Ny], acc);
+                s[j] += acc + sr[j];
+            }
+        }
+    } else
     for (int sub = 0; sub < n; ++sub) {
         const bool odd = sub & 1;
         double* fw = (odd ? fwb1 : fwb0) + Ny + threadIdx.x;
@@ -541,10 +573,9 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
     g.swc = d.swc;
     g.sor = d.sor;
     Fluid fl;
-    fl.swc = d.swc;
     fl.inv_range = 1.0 / (1.0 - d.swc - d.sor);
-    fl.inv_vw = 1.0 / d.vw;
-    fl.inv_vo = 1.0 / d.vo;
+    fl.swc_ir = d.swc * fl.inv_range;
+    fl.mr = d.vw / d.vo;
     const int64_t M = g.M;
     const size_t vec = (size_t)nm * M;
     const size_t nPart = (size_t)nm * g.nTiles;

@@ -172,3 +172,28 @@ def test_extreme_contrast_floor(golden):
             tol = max(SAT_TOL, 4 * eps * p.max() * nT)
             err = np.abs(res.S_hist[i] - ref).max()
             assert err <= tol, (i, refine, err, tol)
+
+
+@pytest.mark.parametrize("sat_block", [0, 1])
+def test_non_default_fluid_and_porosity(sat_block):
+    """Viscosity ratio, irreducible saturations and a porosity field (both transport kernels)."""
+    from historymatching_b200.sim import GridSpec, run_ensemble
+
+    m, grid, logk, cells, rates, prd = _setup(24, 16, 3, seed=9)
+    grid = GridSpec(24, 16, m.Lx, m.Ly, vw=0.8, vo=1.3, swc=0.1, sor=0.15)
+    rng = np.random.RandomState(0)
+    por = 0.6 + 0.4 * rng.rand(24 * 16)
+    S0 = np.full(grid.M, 0.1)
+    nT, dt = 6, 0.02
+    res = run_ensemble(grid, orr.perm_transf(logk), cells, rates, S0, dt, nT, obs_cell=prd, history=True, por=por,
+                       want_substeps=True, sat_block=sat_block)
+    assert not res.status.any()
+    for i in range(3):
+        om = orr.OracleResSim(24, 16, m.Lx, m.Ly, vw=0.8, vo=1.3, swc=0.1, sor=0.15)
+        p = orr.perm_transf(logk[i]).reshape(om.shape)
+        om.K = np.stack([p, p])
+        om.por = por.reshape(om.shape)
+        om.inj_xy, om.prd_xy, om.inj_rates, om.prd_rates = m.inj_xy, m.prd_xy, m.inj_rates, m.prd_rates
+        ref, aux = om.sim(dt, nT, S0, return_aux=True)
+        np.testing.assert_array_equal(res.substeps[i], aux["Nts"])
+        np.testing.assert_allclose(res.S_hist[i], ref, rtol=0, atol=SAT_TOL)
