@@ -43,7 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [
         nvcc_path(),
         "-gencode", "arch=compute_100a,code=sm_100a",
-        "-O3", "-std=c++17", "-lineinfo",
+        "-O3", "-std=c++17", "-lineinfo", *os.environ.get("HM_NVCC_EXTRA", "").split(),
         "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
         "-shared",
         "-o", LIB,

@@ -22,6 +22,8 @@
 // CG itself is two more streamed kernels per iteration (k_cg_spmv 48 B/cell,
 // k_cg_update 48 B/cell).  Members converge independently: a per-member `done`
 // flag makes the CTAs of converged members exit at once.
+#include <type_traits>
+
 #include "hm_sim_common.cuh"
 
 namespace hmsim {
@@ -32,31 +34,55 @@ constexpr int kMaxLevels = 14;
 constexpr int kOnchipCells = 4096;
 constexpr int kOnchipThreads = 1024;
 constexpr int kWcycleMinCells = 64;  // recurse twice into a coarse level with at least this many cells
-// Jacobi sweeps weighted by the roots of the degree-2 Chebyshev polynomial on [1/3, 2] (the
-// spectrum of D^-1 A lies in [0, 2]): same cost as damped Jacobi, markedly better smoothing.
-// Pre-smoothing applies (kW1, kW2), post-smoothing (kW2, kW1), which keeps the cycle symmetric.
-constexpr double kW1 = 0.56950691011;  // 1 / 1.75592
-constexpr double kW2 = 1.73205080757;  // 1 / 0.57735
+// NU Jacobi sweeps weighted by the reciprocal roots of the degree-NU Chebyshev polynomial on
+// [2/8, 2] (the spectrum of D^-1 A lies in [0, 2]): same cost as damped Jacobi, markedly better
+// smoothing.  Pre-smoothing applies the weights in order, post-smoothing in reverse order, which
+// keeps the cycle symmetric (the smoother is a polynomial in D^-1 A either way).
+#ifndef HM_NU
+#define HM_NU 3
+#endif
+constexpr int kNu = HM_NU;
+__device__ __forceinline__ double cheb_w(int i) {
+    if (kNu == 2)  // interval [1/3, 2]
+        return i == 0 ? 1.0 / 1.7559223176554566 : 1.0 / 0.57741101567787674;
+    if (kNu == 3)  // interval [1/4, 2]: 1 / (1.125 + 0.875 cos(pi (2i+1) / 6))
+        return i == 0 ? 1.0 / 1.8827722283113838 : i == 1 ? 1.0 / 1.125 : 1.0 / 0.36722777168861618;
+    // kNu == 4, interval [1/5, 2]: 1 / (1.1 + 0.9 cos(pi (2i+1) / 8))
+    return i == 0 ? 1.0 / 1.9314915792601581 : i == 1 ? 1.0 / 1.4444150891285809
+         : i == 2 ? 1.0 / 0.75558491087141922 : 1.0 / 0.26850842073984186;
+}
 
+// One grid level.  T is the arithmetic type of the preconditioner (double by default; float is an
+// option - the V-cycle only has to be a good, fixed, symmetric approximation of A^-1 and CG itself
+// stays FP64 - that costs ~10 % more iterations on smooth fields and up to 2x on rough ones).  On the top
+// level (TOP) the right-hand side is the FP64 CG residual and the result z is written in FP64.
+template <typename T>
 struct Lvl {
     int nx, ny, M;
     int R, nTiles;
-    const double* TX;
-    const double* TY;
-    const double* dinv;
-    double* b;        // right-hand side (level 0: the CG residual)
-    double* xa;       // iterate after pre-smoothing
-    double* xb;       // iterate after post-smoothing = the level's result (level 0: z)
+    const T* TX;
+    const T* TY;
+    const T* dinv;
+    void* b;   // right-hand side: const double* on the top level, T* below
+    T* xa;     // iterate after pre-smoothing
+    void* xb;  // iterate after post-smoothing = the level's result: double* (z) on the top level, T* below
 };
+
+template <typename T>
+__device__ __forceinline__ T* smem_as() {
+    extern __shared__ __align__(16) unsigned char hm_smem_raw[];
+    return reinterpret_cast<T*>(hm_smem_raw);
+}
 
 // (A x) at one cell.  xr points at the cell's row in a shared tile that has valid (finite) rows
 // above and below; Tx / Ty point at the cell's own low-face transmissibilities.  No boundary
 // tests: boundary faces carry T = 0 and every T array has a zero pad behind the last member, so
 // the high faces Tx[ny] / Ty[1] are always readable and vanish where there is no neighbour.
-__device__ __forceinline__ double stencil(const double* xr, int col, int ny, const double* __restrict__ Tx,
-                                          const double* __restrict__ Ty, bool cell0, double pin) {
-    const double xc = xr[col];
-    double y = Tx[0] * (xc - xr[col - ny]);
+template <typename T>
+__device__ __forceinline__ T stencil(const T* xr, int col, int ny, const T* __restrict__ Tx,
+                                     const T* __restrict__ Ty, bool cell0, T pin) {
+    const T xc = xr[col];
+    T y = Tx[0] * (xc - xr[col - ny]);
     y = fma(Tx[ny], xc - xr[col + ny], y);
     y = fma(Ty[0], xc - xr[col - 1], y);
     y = fma(Ty[1], xc - xr[col + 1], y);
@@ -65,96 +91,132 @@ __device__ __forceinline__ double stencil(const double* xr, int col, int ny, con
 }
 
 // ---- hierarchy ------------------------------------------------------------------------------
-__global__ void k_mg_coarsen(int nm, Lvl f, int cnx, int cny, double* __restrict__ cTX,
-                             double* __restrict__ cTY, double* __restrict__ cdinv,
-                             const double* __restrict__ pin) {
+// FP64 level-0 operator -> arithmetic type of the preconditioner
+template <typename T>
+__global__ void k_mg_cast(int64_t n, const double* __restrict__ a, const double* __restrict__ b,
+                          const double* __restrict__ c, T* __restrict__ oa, T* __restrict__ ob,
+                          T* __restrict__ oc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    oa[i] = (T)a[i];
+    ob[i] = (T)b[i];
+    oc[i] = (T)c[i];
+}
+
+template <typename T>
+__global__ void k_mg_coarsen(int nm, Lvl<T> f, int cnx, int cny, T* __restrict__ cTX, T* __restrict__ cTY,
+                             T* __restrict__ cdinv, const double* __restrict__ pin) {
     const int cM = cnx * cny;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)nm * cM) return;
     const int m = (int)(idx / cM), e = (int)(idx % cM);
     const int I = e / cny, J = e % cny;
-    const double* TX = f.TX + (int64_t)m * f.M;
-    const double* TY = f.TY + (int64_t)m * f.M;
+    const T* TX = f.TX + (int64_t)m * f.M;
+    const T* TY = f.TY + (int64_t)m * f.M;
     const int fi = 2 * I, fj = 2 * J;
     const bool j1 = fj + 1 < f.ny, i1 = fi + 1 < f.nx;
     auto tx = [&](int i) {  // half the sum of the fine x-faces on the low side of fine row i
-        if (i >= f.nx) return 0.0;
-        return 0.5 * (TX[i * f.ny + fj] + (j1 ? TX[i * f.ny + fj + 1] : 0.0));
+        if (i >= f.nx) return (T)0;
+        return (T)0.5 * (TX[i * f.ny + fj] + (j1 ? TX[i * f.ny + fj + 1] : (T)0));
     };
     auto ty = [&](int j) {
-        if (j >= f.ny) return 0.0;
-        return 0.5 * (TY[fi * f.ny + j] + (i1 ? TY[(fi + 1) * f.ny + j] : 0.0));
+        if (j >= f.ny) return (T)0;
+        return (T)0.5 * (TY[fi * f.ny + j] + (i1 ? TY[(fi + 1) * f.ny + j] : (T)0));
     };
-    const double txl = tx(fi), txh = tx(fi + 2), tyl = ty(fj), tyh = ty(fj + 2);
-    double d = tyl + tyh + txl + txh;
-    if (e == 0) d += pin[m];
+    const T txl = tx(fi), txh = tx(fi + 2), tyl = ty(fj), tyh = ty(fj + 2);
+    T d = tyl + tyh + txl + txh;
+    if (e == 0) d += (T)pin[m];
     cTX[idx] = txl;
     cTY[idx] = tyl;
-    cdinv[idx] = 1.0 / d;
+    cdinv[idx] = (T)1 / d;
 }
 
 // ---- streamed level: pre-smoothing + residual + restriction --------------------------------------
-// Rows [r0,r1) of the tile (r0 even).  x1 = w1 D^-1 b on rows [r0-2, r1+2), x2 = x1 + w2 D^-1 (b - A x1)
-// on rows [r0-1, r1+1), residual on the tile rows, 2x2 sums of it to the coarse right-hand side.
-// A warp walks whole grid rows (lanes along the contiguous index): no integer division.
+// Rows [r0,r1) of the tile (r0 even).  Sweep 1 (x = w0 D^-1 b, zero initial guess) covers rows
+// [r0-NU, r1+NU); every further sweep shrinks the range by one row on either side, so after NU
+// sweeps rows [r0-1, r1+1) are exact; then the residual on the tile rows and its 2x2 sums (the
+// coarse right-hand side).  b, the operator and the sweeps ping-pong in shared memory; a warp
+// walks whole grid rows (lanes along the contiguous index): no integer division.
+template <typename T, bool TOP>
 __global__ void __launch_bounds__(kThreads)
-k_mg_down(Lvl f, int cny, double* __restrict__ cb, const double* __restrict__ pin,
-          const int* __restrict__ done) {
-    extern __shared__ double sm[];
+k_mg_down(Lvl<T> f, int cny, T* __restrict__ cb, const double* __restrict__ pin, const int* __restrict__ done) {
+    using TB = typename std::conditional<TOP, double, T>::type;
+    T* sm = smem_as<T>();
     const int m = blockIdx.x / f.nTiles, t = blockIdx.x % f.nTiles;
     if (done[m]) return;
+    constexpr int H = kNu;  // halo rows of the first sweep
     const int ny = f.ny, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nW = kThreads >> 5;
     const int r0 = t * f.R, r1 = min(r0 + f.R, f.nx), rows = r1 - r0;
     const int64_t off = (int64_t)m * f.M;
-    const double* __restrict__ b = f.b + off;
-    const double* __restrict__ dinv = f.dinv + off;
-    const double* __restrict__ TX = f.TX + off;
-    const double* __restrict__ TY = f.TY + off;
-    const double pinv = pin[m];
-    double* x1 = sm;                     // rows r0-2 .. r1+1   -> (rows+4) * ny
-    double* x2 = sm + (f.R + 4) * ny;    // rows r0-1 .. r1     -> (rows+2) * ny
-    for (int lr = warp; lr < rows + 4; lr += nW) {
-        const int row = r0 - 2 + lr;
+    const TB* __restrict__ b = static_cast<const TB*>(f.b) + off;
+    const T* __restrict__ dinv = f.dinv + off;
+    const T* __restrict__ TX = f.TX + off;
+    const T* __restrict__ TY = f.TY + off;
+    const T pinv = (T)pin[m];
+    // FP32: right-hand side and D^-1 of the loaded rows are staged in shared memory as well; in FP64
+    // that would halve the occupancy, they are re-read through L1 instead
+    constexpr bool STAGE = sizeof(T) == 4;
+    const int L = f.R + 2 * H;
+    T* xa = sm;            // all arrays: local row lr <-> grid row r0 - H + lr
+    T* xb = sm + L * ny;
+    T* bs = sm + 2 * L * ny;
+    T* ds = sm + 3 * L * ny;
+    for (int lr = warp; lr < rows + 2 * H; lr += nW) {
+        const int row = r0 - H + lr;
         const bool in = row >= 0 && row < f.nx;
         const int c0 = row * ny;
-        for (int col = lane; col < ny; col += 32) x1[lr * ny + col] = in ? kW1 * dinv[c0 + col] * b[c0 + col] : 0.0;
-    }
-    __syncthreads();
-    for (int lr = warp; lr < rows + 2; lr += nW) {
-        const int row = r0 - 1 + lr;
-        const bool in = row >= 0 && row < f.nx;
-        const int c0 = row * ny;
-        const double* xr = x1 + (lr + 1) * ny;
         for (int col = lane; col < ny; col += 32) {
-            double v = 0.0;
-            if (in) {
-                const int c = c0 + col;
-                v = xr[col] + kW2 * dinv[c] * (b[c] - stencil(xr, col, ny, TX + c, TY + c, c == 0, pinv));
+            const T bv = in ? (T)b[c0 + col] : (T)0, dv = in ? dinv[c0 + col] : (T)0;
+            if (STAGE) {
+                bs[lr * ny + col] = bv;
+                ds[lr * ny + col] = dv;
             }
-            x2[lr * ny + col] = v;
+            xa[lr * ny + col] = (T)cheb_w(0) * dv * bv;
+            xb[lr * ny + col] = (T)0;
         }
     }
     __syncthreads();
-    double* res = x1;  // x1 is dead: reuse for the residual of the tile rows, index (row-r0)*ny+col
+#pragma unroll
+    for (int sw = 1; sw < kNu; ++sw) {  // sweep sw+1 is valid on local rows [sw, rows + 2H - sw)
+        const T w = (T)cheb_w(sw);
+        for (int lr = sw + warp; lr < rows + 2 * H - sw; lr += nW) {
+            const int row = r0 - H + lr;
+            if (row < 0 || row >= f.nx) continue;
+            const int c0 = row * ny;
+            const T* xr = xa + lr * ny;
+            for (int col = lane; col < ny; col += 32) {
+                const int c = c0 + col, li = lr * ny + col;
+                const T dv = STAGE ? ds[li] : dinv[c], bv = STAGE ? bs[li] : (T)b[c];
+                xb[li] = xr[col] + w * dv * (bv - stencil<T>(xr, col, ny, TX + c, TY + c, c == 0, pinv));
+            }
+        }
+        __syncthreads();
+        T* tsw = xa;
+        xa = xb;
+        xb = tsw;
+    }
+    // xa: pre-smoothed iterate, exact on local rows [H-1, H+rows+1); residual of the tile rows -> xb
     for (int lr = warp; lr < rows; lr += nW) {
         const int c0 = (r0 + lr) * ny;
-        const double* xr = x2 + (lr + 1) * ny;
+        const T* xr = xa + (lr + H) * ny;
         for (int col = lane; col < ny; col += 32) {
             const int c = c0 + col;
             f.xa[off + c] = xr[col];
-            res[lr * ny + col] = b[c] - stencil(xr, col, ny, TX + c, TY + c, c == 0, pinv);
+            const T bv = STAGE ? bs[(lr + H) * ny + col] : (T)b[c];
+            xb[lr * ny + col] = bv - stencil<T>(xr, col, ny, TX + c, TY + c, c == 0, pinv);
         }
     }
     __syncthreads();
+    const T* res = xb;
     const int crows = (rows + 1) / 2, cM = ((f.nx + 1) / 2) * cny;
     for (int I = warp; I < crows; I += nW) {
         const int lr = 2 * I;
         const bool two = lr + 1 < rows;
-        double* out = cb + (int64_t)m * cM + (int64_t)(r0 / 2 + I) * cny;
+        T* out = cb + (int64_t)m * cM + (int64_t)(r0 / 2 + I) * cny;
         for (int J = lane; J < cny; J += 32) {
             const int col = 2 * J;
             const bool cc = col + 1 < ny;
-            double sacc = res[lr * ny + col];
+            T sacc = res[lr * ny + col];
             if (cc) sacc += res[lr * ny + col + 1];
             if (two) {
                 sacc += res[(lr + 1) * ny + col];
@@ -165,64 +227,84 @@ k_mg_down(Lvl f, int cny, double* __restrict__ cb, const double* __restrict__ pi
     }
 }
 
-// ---- streamed level: prolongation + post-smoothing (+ (r,z) on level 0) ----------------------------
-template <bool DOT>
+// ---- streamed level: prolongation + post-smoothing (+ (r,z) on the top level) ----------------------
+// x = xa + P xc on rows [r0-NU, r1+NU), then NU sweeps (weights in reverse order) on shrinking row
+// ranges; the last sweep covers exactly the tile rows and is written to xb.
+template <typename T, bool TOP>
 __global__ void __launch_bounds__(kThreads)
-k_mg_up(Lvl f, int cny, const double* __restrict__ cx, const double* __restrict__ pin,
+k_mg_up(Lvl<T> f, int cny, const T* __restrict__ cx, const double* __restrict__ pin,
         const int* __restrict__ done, double* __restrict__ part_rz) {
-    extern __shared__ double sm[];
+    using TB = typename std::conditional<TOP, double, T>::type;
+    T* sm = smem_as<T>();
     __shared__ double red[32];
     const int m = blockIdx.x / f.nTiles, t = blockIdx.x % f.nTiles;
     if (done[m]) return;
+    constexpr int H = kNu;
     const int ny = f.ny, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nW = kThreads >> 5;
     const int r0 = t * f.R, r1 = min(r0 + f.R, f.nx), rows = r1 - r0;
     const int64_t off = (int64_t)m * f.M;
     const int cM = ((f.nx + 1) / 2) * cny;
-    const double* __restrict__ b = f.b + off;
-    const double* __restrict__ dinv = f.dinv + off;
-    const double* __restrict__ TX = f.TX + off;
-    const double* __restrict__ TY = f.TY + off;
-    const double* __restrict__ xa = f.xa + off;
-    const double* __restrict__ xc = cx + (int64_t)m * cM;
-    const double pinv = pin[m];
-    double* x0 = sm;                     // rows r0-2 .. r1+1
-    double* x3 = sm + (f.R + 4) * ny;    // rows r0-1 .. r1
-    for (int lr = warp; lr < rows + 4; lr += nW) {
-        const int row = r0 - 2 + lr;
-        const bool in = row >= 0 && row < f.nx;
-        const double* xar = xa + row * ny;
-        const double* xcr = xc + (row >> 1) * cny;
-        for (int col = lane; col < ny; col += 32) x0[lr * ny + col] = in ? xar[col] + xcr[col >> 1] : 0.0;
-    }
-    __syncthreads();
-    for (int lr = warp; lr < rows + 2; lr += nW) {
-        const int row = r0 - 1 + lr;
+    const TB* __restrict__ b = static_cast<const TB*>(f.b) + off;
+    TB* __restrict__ xout = static_cast<TB*>(f.xb) + off;
+    const T* __restrict__ dinv = f.dinv + off;
+    const T* __restrict__ TX = f.TX + off;
+    const T* __restrict__ TY = f.TY + off;
+    const T* __restrict__ xin = f.xa + off;
+    const T* __restrict__ xc = cx + (int64_t)m * cM;
+    const T pinv = (T)pin[m];
+    constexpr bool STAGE = sizeof(T) == 4;
+    const int L = f.R + 2 * H;
+    T* xa = sm;
+    T* xb = sm + L * ny;
+    T* bs = sm + 2 * L * ny;
+    T* ds = sm + 3 * L * ny;
+    for (int lr = warp; lr < rows + 2 * H; lr += nW) {
+        const int row = r0 - H + lr;
         const bool in = row >= 0 && row < f.nx;
         const int c0 = row * ny;
-        const double* xr = x0 + (lr + 1) * ny;
+        const T* xcr = xc + (row >> 1) * cny;
         for (int col = lane; col < ny; col += 32) {
-            double v = 0.0;
-            if (in) {
-                const int c = c0 + col;
-                v = xr[col] + kW2 * dinv[c] * (b[c] - stencil(xr, col, ny, TX + c, TY + c, c == 0, pinv));
+            if (STAGE) {
+                bs[lr * ny + col] = in ? (T)b[c0 + col] : (T)0;
+                ds[lr * ny + col] = in ? dinv[c0 + col] : (T)0;
             }
-            x3[lr * ny + col] = v;
+            xa[lr * ny + col] = in ? xin[c0 + col] + xcr[col >> 1] : (T)0;
+            xb[lr * ny + col] = (T)0;
         }
     }
     __syncthreads();
+#pragma unroll
+    for (int sw = 0; sw < kNu - 1; ++sw) {  // sweep sw+1 is valid on local rows [sw+1, rows + 2H - sw - 1)
+        const T w = (T)cheb_w(kNu - 1 - sw);
+        for (int lr = sw + 1 + warp; lr < rows + 2 * H - sw - 1; lr += nW) {
+            const int row = r0 - H + lr;
+            if (row < 0 || row >= f.nx) continue;
+            const int c0 = row * ny;
+            const T* xr = xa + lr * ny;
+            for (int col = lane; col < ny; col += 32) {
+                const int c = c0 + col, li = lr * ny + col;
+                const T dv = STAGE ? ds[li] : dinv[c], bv = STAGE ? bs[li] : (T)b[c];
+                xb[li] = xr[col] + w * dv * (bv - stencil<T>(xr, col, ny, TX + c, TY + c, c == 0, pinv));
+            }
+        }
+        __syncthreads();
+        T* tsw = xa;
+        xa = xb;
+        xb = tsw;
+    }
     double dot = 0.0;
     for (int lr = warp; lr < rows; lr += nW) {
         const int c0 = (r0 + lr) * ny;
-        const double* xr = x3 + (lr + 1) * ny;
+        const T* xr = xa + (lr + H) * ny;
         for (int col = lane; col < ny; col += 32) {
-            const int c = c0 + col;
-            const double bc = b[c];
-            const double v = xr[col] + kW1 * dinv[c] * (bc - stencil(xr, col, ny, TX + c, TY + c, c == 0, pinv));
-            f.xb[off + c] = v;
-            if (DOT) dot = fma(bc, v, dot);
+            const int c = c0 + col, li = (lr + H) * ny + col;
+            const T dv = STAGE ? ds[li] : dinv[c], bv = STAGE ? bs[li] : (T)b[c];
+            const T v = xr[col] + (T)cheb_w(0) * dv * (bv - stencil<T>(xr, col, ny, TX + c, TY + c, c == 0, pinv));
+            xout[c] = (TB)v;
+            if (TOP) dot = fma((double)b[c], (double)v, dot);
         }
     }
-    if (DOT) {
+    if (TOP) {
         dot = block_sum(dot, red);
         if (threadIdx.x == 0) part_rz[(int64_t)m * f.nTiles + t] = dot;
     }
@@ -233,15 +315,16 @@ struct OnchipMeta {
     int n;                  // number of on-chip levels
     int nx[kMaxLevels], ny[kMaxLevels], M[kMaxLevels], off[kMaxLevels];
     float inv_ny[kMaxLevels];
-    const double* TX[kMaxLevels];
-    const double* TY[kMaxLevels];
-    const double* dinv[kMaxLevels];
+    const void* TX[kMaxLevels];
+    const void* TY[kMaxLevels];
+    const void* dinv[kMaxLevels];
     int total;              // total cells over the on-chip levels
     int wmin;               // W-cycle: visit a coarse level twice if it has >= wmin cells (V-cycle: INT_MAX)
 };
 
+template <typename T>
 struct OnchipSmem {
-    double *X, *B, *TX, *TY, *DV;
+    T *X, *B, *TX, *TY, *DV;
 };
 
 __device__ __forceinline__ void cell_ij(int e, int ny, float inv_ny, int& i, int& j) {
@@ -249,11 +332,12 @@ __device__ __forceinline__ void cell_ij(int e, int ny, float inv_ny, int& i, int
     j = e - i * ny;
 }
 
-__device__ __forceinline__ double onchip_Ax(const OnchipMeta& mt, const OnchipSmem& s, int l, int e, int i, int j,
-                                            double pin) {
+template <typename T>
+__device__ __forceinline__ T onchip_Ax(const OnchipMeta& mt, const OnchipSmem<T>& s, int l, int e, int i, int j,
+                                       T pin) {
     const int ny = mt.ny[l], o = mt.off[l] + e;
-    const double xc = s.X[o];
-    double y = 0.0;
+    const T xc = s.X[o];
+    T y = 0;
     if (i > 0) y = s.TX[o] * (xc - s.X[o - ny]);
     if (i < mt.nx[l] - 1) y = fma(s.TX[o + ny], xc - s.X[o + ny], y);
     if (j > 0) y = fma(s.TY[o], xc - s.X[o - 1], y);
@@ -262,22 +346,23 @@ __device__ __forceinline__ double onchip_Ax(const OnchipMeta& mt, const OnchipSm
     return y;
 }
 
-// nsweep damped-Jacobi sweeps on level l, in place (new values staged in registers)
-__device__ __forceinline__ void onchip_smooth(const OnchipMeta& mt, const OnchipSmem& s, int l, double pin,
-                                              int nsweep, double wa, double wb) {
+// nsweep weighted-Jacobi sweeps on level l, in place (new values staged in registers)
+template <typename T>
+__device__ __forceinline__ void onchip_smooth(const OnchipMeta& mt, const OnchipSmem<T>& s, int l, T pin,
+                                              int nsweep, bool reverse) {
     constexpr int PER = kOnchipCells / kOnchipThreads;
     const int M = mt.M[l], ny = mt.ny[l], o = mt.off[l];
     const float inv = mt.inv_ny[l];
     for (int sw = 0; sw < nsweep; ++sw) {
-        const double wgt = (sw & 1) ? wb : wa;
-        double xn[PER];
+        const T wgt = (T)cheb_w(reverse ? (kNu - 1 - sw % kNu) : sw % kNu);
+        T xn[PER];
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
             const int e = threadIdx.x + k * kOnchipThreads;
             if (e < M) {
                 int i, j;
                 cell_ij(e, ny, inv, i, j);
-                xn[k] = s.X[o + e] + wgt * s.DV[o + e] * (s.B[o + e] - onchip_Ax(mt, s, l, e, i, j, pin));
+                xn[k] = s.X[o + e] + wgt * s.DV[o + e] * (s.B[o + e] - onchip_Ax<T>(mt, s, l, e, i, j, pin));
             }
         }
         __syncthreads();
@@ -292,14 +377,15 @@ __device__ __forceinline__ void onchip_smooth(const OnchipMeta& mt, const Onchip
 
 // Residual of level l restricted to level l+1 (each coarse thread evaluates its own children);
 // the coarse iterate is reset to zero.
-__device__ __forceinline__ void onchip_restrict(const OnchipMeta& mt, const OnchipSmem& s, int l, double pin) {
+template <typename T>
+__device__ __forceinline__ void onchip_restrict(const OnchipMeta& mt, const OnchipSmem<T>& s, int l, T pin) {
     const int ny = mt.ny[l], nx = mt.nx[l], o = mt.off[l];
     const int cM = mt.M[l + 1], cny = mt.ny[l + 1], co = mt.off[l + 1];
     const float cinv = mt.inv_ny[l + 1];
     for (int e = threadIdx.x; e < cM; e += kOnchipThreads) {
         int ci, cj;
         cell_ij(e, cny, cinv, ci, cj);
-        double r = 0.0;
+        T r = 0;
 #pragma unroll
         for (int di = 0; di < 2; ++di)
 #pragma unroll
@@ -307,16 +393,17 @@ __device__ __forceinline__ void onchip_restrict(const OnchipMeta& mt, const Onch
                 const int i = 2 * ci + di, j = 2 * cj + dj;
                 if (i < nx && j < ny) {
                     const int fe = i * ny + j;
-                    r += s.B[o + fe] - onchip_Ax(mt, s, l, fe, i, j, pin);
+                    r += s.B[o + fe] - onchip_Ax<T>(mt, s, l, fe, i, j, pin);
                 }
             }
         s.B[co + e] = r;
-        s.X[co + e] = 0.0;
+        s.X[co + e] = 0;
     }
     __syncthreads();
 }
 
-__device__ __forceinline__ void onchip_prolong(const OnchipMeta& mt, const OnchipSmem& s, int l) {
+template <typename T>
+__device__ __forceinline__ void onchip_prolong(const OnchipMeta& mt, const OnchipSmem<T>& s, int l) {
     const int M = mt.M[l], ny = mt.ny[l], o = mt.off[l], cny = mt.ny[l + 1], co = mt.off[l + 1];
     const float inv = mt.inv_ny[l];
     for (int e = threadIdx.x; e < M; e += kOnchipThreads) {
@@ -330,13 +417,14 @@ __device__ __forceinline__ void onchip_prolong(const OnchipMeta& mt, const Onchi
 // One CTA per member runs the cycle on the shared-memory hierarchy.  The cycle (V, or W on the
 // levels of at least `wmin` cells) is an explicit state machine: `left` packs, 4 bits per level,
 // how many cycles are still to be run on that level; every control variable is CTA-uniform.
+template <typename T>
 __global__ void __launch_bounds__(kOnchipThreads, 1)
-k_mg_onchip(const __grid_constant__ OnchipMeta mt, const double* __restrict__ b_in, double* __restrict__ x_out,
+k_mg_onchip(const __grid_constant__ OnchipMeta mt, const T* __restrict__ b_in, T* __restrict__ x_out,
             const double* __restrict__ pin, const int* __restrict__ done) {
-    extern __shared__ double sm[];
+    T* sm = smem_as<T>();
     const int m = blockIdx.x;
     if (done[m]) return;
-    OnchipSmem s;
+    OnchipSmem<T> s;
     s.X = sm;
     s.B = sm + mt.total;
     s.TX = sm + 2 * mt.total;
@@ -344,19 +432,22 @@ k_mg_onchip(const __grid_constant__ OnchipMeta mt, const double* __restrict__ b_
     s.DV = sm + 4 * mt.total;
     for (int l = 0; l < mt.n; ++l) {
         const int64_t g = (int64_t)m * mt.M[l];
+        const T* tx = static_cast<const T*>(mt.TX[l]) + g;
+        const T* ty = static_cast<const T*>(mt.TY[l]) + g;
+        const T* dv = static_cast<const T*>(mt.dinv[l]) + g;
         for (int e = threadIdx.x; e < mt.M[l]; e += kOnchipThreads) {
-            s.TX[mt.off[l] + e] = mt.TX[l][g + e];
-            s.TY[mt.off[l] + e] = mt.TY[l][g + e];
-            s.DV[mt.off[l] + e] = mt.dinv[l][g + e];
+            s.TX[mt.off[l] + e] = tx[e];
+            s.TY[mt.off[l] + e] = ty[e];
+            s.DV[mt.off[l] + e] = dv[e];
         }
     }
     const int M0 = mt.M[0];
     for (int e = threadIdx.x; e < M0; e += kOnchipThreads) {
         s.B[e] = b_in[(int64_t)m * M0 + e];
-        s.X[e] = 0.0;
+        s.X[e] = 0;
     }
     __syncthreads();
-    const double pinv = pin[m];
+    const T pinv = (T)pin[m];
     unsigned long long left = (M0 >= mt.wmin) ? 2ull : 1ull;
     int l = 0;
     bool descend = true;
@@ -367,13 +458,13 @@ k_mg_onchip(const __grid_constant__ OnchipMeta mt, const double* __restrict__ b_
                     if (threadIdx.x == 0) s.X[mt.off[l]] = s.B[mt.off[l]] * s.DV[mt.off[l]];
                     __syncthreads();
                 } else {
-                    onchip_smooth(mt, s, l, pinv, 8, kW1, kW2);
+                    onchip_smooth<T>(mt, s, l, pinv, 3 * kNu, false);
                 }
                 left -= 1ull << (4 * l);
                 descend = false;
             } else {
-                onchip_smooth(mt, s, l, pinv, 2, kW1, kW2);
-                onchip_restrict(mt, s, l, pinv);
+                onchip_smooth<T>(mt, s, l, pinv, kNu, false);
+                onchip_restrict<T>(mt, s, l, pinv);
                 ++l;
                 left |= ((mt.M[l] >= mt.wmin) ? 2ull : 1ull) << (4 * l);
             }
@@ -384,8 +475,8 @@ k_mg_onchip(const __grid_constant__ OnchipMeta mt, const double* __restrict__ b_
                 break;
             } else {
                 --l;
-                onchip_prolong(mt, s, l);
-                onchip_smooth(mt, s, l, pinv, 2, kW2, kW1);
+                onchip_prolong<T>(mt, s, l);
+                onchip_smooth<T>(mt, s, l, pinv, kNu, true);
                 left -= 1ull << (4 * l);
             }
         }
@@ -575,6 +666,151 @@ k_cg_update(Geo g, double* __restrict__ X, double* __restrict__ Rv, double* __re
     }
 }
 
+// ---- multigrid hierarchy of one solve (host side) ---------------------------------------------------
+template <typename T>
+struct MgHierarchy {
+    Lvl<T> lv[kMaxLevels];
+    int nLev = 0, firstOn = 0, nm = 0;
+    OnchipMeta mt{};
+    size_t smemOn = 0;
+    const double* pin = nullptr;
+    int* done = nullptr;
+    double* part_rz = nullptr;
+    size_t nPart = 0;
+
+    size_t smem_level(int l) const { return (size_t)(sizeof(T) == 4 ? 4 : 2) * (lv[l].R + 2 * kNu) * lv[l].ny * sizeof(T); }
+
+    int build(hm_ctx* ctx, const Geo& g, int nm_, const double* TXl, const double* TYl, const double* dinv,
+              const double* pin_, double* Rv, double* Z, bool wcycle, int* done_, double* part_rz_, size_t nPart_) {
+        cudaStream_t st = ctx->stream;
+        nm = nm_;
+        pin = pin_;
+        done = done_;
+        part_rz = part_rz_;
+        nPart = nPart_;
+        const char* tag = sizeof(T) == 4 ? "f" : "d";
+        int nx = g.Nx, ny = g.Ny;
+        nLev = 0;
+        while (true) {
+            Lvl<T>& L = lv[nLev];
+            L.nx = nx;
+            L.ny = ny;
+            L.M = nx * ny;
+            if (nLev == 0) {  // level 0 shares the CG tiling (its (r,z) partials are summed per CG tile)
+                L.R = g.R;
+            } else {
+                int R = std::max(2, std::min(nx, 4096 / ny));
+                L.R = std::max(2, R & ~1);
+            }
+            L.nTiles = (nx + L.R - 1) / L.R;
+            ++nLev;
+            if ((nx == 1 && ny == 1) || nLev == kMaxLevels) break;
+            nx = (nx + 1) / 2;
+            ny = (ny + 1) / 2;
+        }
+        firstOn = 1;
+        while (firstOn < nLev && lv[firstOn].M > kOnchipCells) ++firstOn;
+        HM_REQUIRE(firstOn < nLev, "grid too large for the multigrid hierarchy");
+        char name[40];
+        for (int l = 0; l < nLev; ++l) {
+            const size_t n = (size_t)nm * lv[l].M;
+            T *tx, *ty, *dv;
+            snprintf(name, sizeof name, "mg%s.TX%d", tag, l);
+            HM_CHECK(ctx->ws.get(name, n + (size_t)lv[l].ny, &tx));  // + zero pads, see stencil()
+            snprintf(name, sizeof name, "mg%s.TY%d", tag, l);
+            HM_CHECK(ctx->ws.get(name, n + 1, &ty));
+            snprintf(name, sizeof name, "mg%s.dv%d", tag, l);
+            HM_CHECK(ctx->ws.get(name, n, &dv));
+            HM_CUDA(cudaMemsetAsync(tx + n, 0, (size_t)lv[l].ny * sizeof(T), st));
+            HM_CUDA(cudaMemsetAsync(ty + n, 0, sizeof(T), st));
+            lv[l].TX = tx;
+            lv[l].TY = ty;
+            lv[l].dinv = dv;
+            lv[l].b = nullptr;
+            lv[l].xa = nullptr;
+            lv[l].xb = nullptr;
+            if (l == 0) {
+                k_mg_cast<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((int64_t)n, TXl, TYl, dinv, tx, ty, dv);
+                lv[0].b = Rv;
+                lv[0].xb = Z;
+                snprintf(name, sizeof name, "mg%s.xa0", tag);
+                HM_CHECK(ctx->ws.get(name, n, &lv[0].xa));
+            } else {
+                if (l <= firstOn) {  // streamed levels and the first on-chip level exchange b / x through HBM
+                    T *bq, *xq;
+                    snprintf(name, sizeof name, "mg%s.b%d", tag, l);
+                    HM_CHECK(ctx->ws.get(name, n, &bq));
+                    lv[l].b = bq;
+                    snprintf(name, sizeof name, "mg%s.xb%d", tag, l);
+                    HM_CHECK(ctx->ws.get(name, n, &xq));
+                    lv[l].xb = xq;
+                    if (l < firstOn) {
+                        snprintf(name, sizeof name, "mg%s.xa%d", tag, l);
+                        HM_CHECK(ctx->ws.get(name, n, &lv[l].xa));
+                    }
+                }
+                k_mg_coarsen<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(nm, lv[l - 1], lv[l].nx, lv[l].ny, tx, ty,
+                                                                              dv, pin);
+            }
+            ctx->sim_stats.kernel_launches += 1;
+        }
+        mt = OnchipMeta{};
+        mt.n = nLev - firstOn;
+        int o = 0;
+        for (int i = 0; i < mt.n; ++i) {
+            const Lvl<T>& L = lv[firstOn + i];
+            mt.nx[i] = L.nx;
+            mt.ny[i] = L.ny;
+            mt.M[i] = L.M;
+            mt.off[i] = o;
+            mt.inv_ny[i] = 1.0f / (float)L.ny;
+            mt.TX[i] = L.TX;
+            mt.TY[i] = L.TY;
+            mt.dinv[i] = L.dinv;
+            o += L.M;
+        }
+        mt.total = o;
+        mt.wmin = wcycle ? kWcycleMinCells : 0x7fffffff;
+        smemOn = (size_t)5 * o * sizeof(T);
+        HM_CUDA(cudaFuncSetAttribute(k_mg_onchip<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemOn));
+        size_t smax = 0;
+        for (int l = 0; l < firstOn; ++l) smax = std::max(smax, smem_level(l));
+        HM_REQUIRE(smax <= 200 * 1024, "row tile of a streamed multigrid level exceeds shared memory");
+        if (smax > 40 * 1024) {
+            HM_CUDA(cudaFuncSetAttribute(k_mg_down<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+            HM_CUDA(cudaFuncSetAttribute(k_mg_down<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+            HM_CUDA(cudaFuncSetAttribute(k_mg_up<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+            HM_CUDA(cudaFuncSetAttribute(k_mg_up<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+        }
+        return HM_OK;
+    }
+
+    // z = M^-1 r by one multigrid cycle; the (r,z) partials go to the `parity` slot
+    void apply(hm_ctx* ctx, int parity) {
+        cudaStream_t st = ctx->stream;
+        for (int l = 0; l < firstOn; ++l) {
+            T* cb = static_cast<T*>(lv[l + 1].b);
+            if (l == 0)
+                k_mg_down<T, true><<<nm * lv[l].nTiles, kThreads, smem_level(l), st>>>(lv[l], lv[l + 1].ny, cb, pin, done);
+            else
+                k_mg_down<T, false><<<nm * lv[l].nTiles, kThreads, smem_level(l), st>>>(lv[l], lv[l + 1].ny, cb, pin, done);
+        }
+        k_mg_onchip<T><<<nm, kOnchipThreads, smemOn, st>>>(mt, static_cast<const T*>(lv[firstOn].b),
+                                                            static_cast<T*>(lv[firstOn].xb), pin, done);
+        for (int l = firstOn - 1; l >= 0; --l) {
+            const T* cx = static_cast<const T*>(lv[l + 1].xb);
+            if (l == 0)
+                k_mg_up<T, true><<<nm * lv[l].nTiles, kThreads, smem_level(l), st>>>(lv[l], lv[l + 1].ny, cx, pin, done,
+                                                                                      part_rz + parity * nPart);
+            else
+                k_mg_up<T, false><<<nm * lv[l].nTiles, kThreads, smem_level(l), st>>>(lv[l], lv[l + 1].ny, cx, pin, done,
+                                                                                       nullptr);
+        }
+        ctx->sim_stats.kernel_launches += 2 * firstOn + 1;
+        ctx->sim_stats.cg_kernel_launches += 2 * firstOn + 1;
+    }
+};
+
 }  // namespace
 
 // ---- host side -----------------------------------------------------------------------------------
@@ -608,115 +844,21 @@ int pressure_solve(hm_ctx* ctx, const Geo& g, const Wells& w, int step, int nm, 
         HM_CUDA(cudaFuncSetAttribute(k_cg_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     }
 
-    // ---- multigrid hierarchy ------------------------------------------------------------------
-    Lvl lv[kMaxLevels];
-    int nLev = 0, firstOn = 0;
-    OnchipMeta mt{};
-    size_t smemOn = 0;
+    // ---- multigrid hierarchy: FP64 V-cycle (precond 0), FP64 W-cycle (2) or FP32 V-cycle (3) ------------
+    MgHierarchy<float> mgf;
+    MgHierarchy<double> mgd;
+    const bool mg32 = precond == 3;
     if (!jacobi) {
-        int nx = g.Nx, ny = g.Ny;
-        while (true) {
-            Lvl& L = lv[nLev];
-            L.nx = nx;
-            L.ny = ny;
-            L.M = nx * ny;
-            if (nLev == 0) {  // level 0 shares the CG tiling (its (r,z) partials are summed per CG tile)
-                L.R = g.R;
-            } else {
-                int R = std::max(2, std::min(nx, 4096 / ny));
-                L.R = std::max(2, R & ~1);
-            }
-            L.nTiles = (nx + L.R - 1) / L.R;
-            ++nLev;
-            if ((nx == 1 && ny == 1) || nLev == kMaxLevels) break;
-            nx = (nx + 1) / 2;
-            ny = (ny + 1) / 2;
-        }
-        firstOn = 1;
-        while (firstOn < nLev && lv[firstOn].M > kOnchipCells) ++firstOn;
-        HM_REQUIRE(firstOn < nLev, "grid too large for the multigrid hierarchy");
-        lv[0].TX = TXl;
-        lv[0].TY = TYl;
-        lv[0].dinv = dinv;
-        lv[0].b = Rv;
-        HM_CHECK(ctx->ws.get("mg.xa0", vec, &lv[0].xa));
-        lv[0].xb = Z;
-        for (int l = 1; l < nLev; ++l) {
-            char name[32];
-            const size_t n = (size_t)nm * lv[l].M;
-            double *tx, *ty, *dv, *bq;
-            snprintf(name, sizeof name, "mg.TX%d", l);
-            HM_CHECK(ctx->ws.get(name, n + (size_t)lv[l].ny, &tx));  // + zero pads, see stencil()
-            snprintf(name, sizeof name, "mg.TY%d", l);
-            HM_CHECK(ctx->ws.get(name, n + 1, &ty));
-            HM_CUDA(cudaMemsetAsync(tx + n, 0, (size_t)lv[l].ny * sizeof(double), st));
-            HM_CUDA(cudaMemsetAsync(ty + n, 0, sizeof(double), st));
-            snprintf(name, sizeof name, "mg.dv%d", l);
-            HM_CHECK(ctx->ws.get(name, n, &dv));
-            lv[l].TX = tx;
-            lv[l].TY = ty;
-            lv[l].dinv = dv;
-            lv[l].b = nullptr;
-            lv[l].xa = lv[l].xb = nullptr;
-            if (l <= firstOn) {  // streamed levels and the first on-chip level exchange b / x through HBM
-                snprintf(name, sizeof name, "mg.b%d", l);
-                HM_CHECK(ctx->ws.get(name, n, &bq));
-                lv[l].b = bq;
-                snprintf(name, sizeof name, "mg.xb%d", l);
-                HM_CHECK(ctx->ws.get(name, n, &lv[l].xb));
-                if (l < firstOn) {
-                    snprintf(name, sizeof name, "mg.xa%d", l);
-                    HM_CHECK(ctx->ws.get(name, n, &lv[l].xa));
-                }
-            }
-            const int64_t tot = (int64_t)nm * lv[l].M;
-            k_mg_coarsen<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(nm, lv[l - 1], lv[l].nx, lv[l].ny, tx, ty, dv, pin);
-            ctx->sim_stats.kernel_launches += 1;
-        }
-        mt.n = nLev - firstOn;
-        int o = 0;
-        for (int i = 0; i < mt.n; ++i) {
-            const Lvl& L = lv[firstOn + i];
-            mt.nx[i] = L.nx;
-            mt.ny[i] = L.ny;
-            mt.M[i] = L.M;
-            mt.off[i] = o;
-            mt.inv_ny[i] = 1.0f / (float)L.ny;
-            mt.TX[i] = L.TX;
-            mt.TY[i] = L.TY;
-            mt.dinv[i] = L.dinv;
-            o += L.M;
-        }
-        mt.total = o;
-        mt.wmin = precond == 2 ? kWcycleMinCells : 0x7fffffff;
-        smemOn = (size_t)5 * o * sizeof(double);
-        HM_CUDA(cudaFuncSetAttribute(k_mg_onchip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemOn));
-        for (int l = 0; l < firstOn; ++l) {
-            const size_t s2 = (size_t)(2 * lv[l].R + 6) * lv[l].ny * sizeof(double);
-            if (s2 > 48 * 1024) {
-                HM_CUDA(cudaFuncSetAttribute(k_mg_down, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
-                HM_CUDA(cudaFuncSetAttribute(k_mg_up<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
-                HM_CUDA(cudaFuncSetAttribute(k_mg_up<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
-            }
-        }
+        if (mg32)
+            HM_CHECK(mgf.build(ctx, g, nm, TXl, TYl, dinv, pin, Rv, Z, false, done, part_rz, nPart));
+        else
+            HM_CHECK(mgd.build(ctx, g, nm, TXl, TYl, dinv, pin, Rv, Z, precond == 2, done, part_rz, nPart));
     }
-    auto precondition = [&](int parity) {  // z = M^-1 r by one multigrid cycle; (r,z) partials -> parity slot
-        for (int l = 0; l < firstOn; ++l) {
-            const size_t s2 = (size_t)(2 * lv[l].R + 6) * lv[l].ny * sizeof(double);
-            k_mg_down<<<nm * lv[l].nTiles, kThreads, s2, st>>>(lv[l], lv[l + 1].ny, lv[l + 1].b, pin, done);
-        }
-        k_mg_onchip<<<nm, kOnchipThreads, smemOn, st>>>(mt, lv[firstOn].b, lv[firstOn].xb, pin, done);
-        for (int l = firstOn - 1; l >= 0; --l) {
-            const size_t s2 = (size_t)(2 * lv[l].R + 6) * lv[l].ny * sizeof(double);
-            if (l == 0)
-                k_mg_up<true><<<nm * lv[l].nTiles, kThreads, s2, st>>>(lv[l], lv[l + 1].ny, lv[l + 1].xb, pin, done,
-                                                                        part_rz + parity * nPart);
-            else
-                k_mg_up<false><<<nm * lv[l].nTiles, kThreads, s2, st>>>(lv[l], lv[l + 1].ny, lv[l + 1].xb, pin, done,
-                                                                         nullptr);
-        }
-        ctx->sim_stats.kernel_launches += 2 * firstOn + 1;
-        ctx->sim_stats.cg_kernel_launches += 2 * firstOn + 1;
+    auto precondition = [&](int parity) {
+        if (mg32)
+            mgf.apply(ctx, parity);
+        else
+            mgd.apply(ctx, parity);
     };
     // tiles start on even rows so that the 2x2 aggregates never straddle two tiles
     if (!jacobi) HM_REQUIRE(g.R % 2 == 0 || g.nTiles == 1, "level-0 tile height must be even");

@@ -521,6 +521,15 @@ __global__ void k_member_status(int n_members, int M, const double* __restrict__
         status[m] = (cg_fail[m] ? HM_MEMBER_CG_NOT_CONVERGED : 0) | (bad ? HM_MEMBER_NON_FINITE : 0);
 }
 
+// warm start of the next pressure solve: linear extrapolation in time, P <- 2 P - Pprev, Pprev <- P
+__global__ void k_extrapolate(int64_t n, double* __restrict__ P, double* __restrict__ Pprev) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double p = P[i];
+    P[i] = 2.0 * p - Pprev[i];
+    Pprev[i] = p;
+}
+
 __global__ void k_mark_unconverged(int n_members, const int* __restrict__ done, int* __restrict__ cg_fail) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m < n_members && !done[m]) cg_fail[m] = 1;
@@ -587,6 +596,8 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
     HM_CHECK(ctx->ws.get("sim.TYl", vec + 1, &TYl));
     HM_CHECK(ctx->ws.get("sim.dinv", vec, &dinv));
     HM_CHECK(ctx->ws.get("sim.P", vec, &P));
+    double* Pprev;
+    HM_CHECK(ctx->ws.get("sim.Pprev", vec, &Pprev));
     HM_CHECK(ctx->ws.get("sim.Vxl", vec + (size_t)d.Ny, &Vxl));  // + zero pad, see sat_tile_body
     HM_CHECK(ctx->ws.get("sim.Vyl", vec + 1, &Vyl));
     HM_CHECK(ctx->ws.get("sim.Sa", vec, &Sa));
@@ -661,6 +672,12 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
                                                      TYl, dinv, pin);
         timer.mark(1);
         HM_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(int), st));
+        if (step >= 2 && d.reserved != 1) {  // P holds P_{k-1}, Pprev holds P_{k-2}
+            k_extrapolate<<<copy_blocks, 256, 0, st>>>((int64_t)vec, P, Pprev);
+            ctx->sim_stats.kernel_launches += 1;
+        } else if (step == 1) {
+            HM_CUDA(cudaMemcpyAsync(Pprev, P, vec * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        }
         int k = 0;
         bool all_done = false;
         HM_CHECK(pressure_solve(ctx, g, w, step, nm, TXl, TYl, dinv, pin, P, rtol, max_iter, d.precond, done, iters,
@@ -752,7 +769,8 @@ int validate(const hm_sim_desc& d) {
     HM_REQUIRE(d.n_steps >= 0 && d.dt > 0, "dt, n_steps");
     HM_REQUIRE(d.n_obs == 0 || d.obs_cell, "obs_cell");
     HM_REQUIRE(d.Ny <= 1024, "Ny <= 1024 (row tiles of at least two grid rows must fit 2048 cells)");
-    HM_REQUIRE(d.precond >= 0 && d.precond <= 2, "precond: 0 = multigrid V-cycle, 1 = Jacobi, 2 = multigrid W-cycle");
+    HM_REQUIRE(d.precond >= 0 && d.precond <= 3,
+               "precond: 0 = multigrid V-cycle, 1 = Jacobi, 2 = multigrid W-cycle, 3 = multigrid V-cycle in FP32");
     return HM_OK;
 }
 

@@ -100,7 +100,8 @@ typedef struct hm_sim_desc {
     double cg_rtol;      /* <=0: default 1e-12 (||r|| <= rtol ||q||) */
     int32_t cg_max_iter; /* <=0: default 100*(Nx+Ny)+200 */
     int32_t chunk_members; /* <=0: all members in one launch wave */
-    int32_t precond;       /* pressure preconditioner: 0 = multigrid V-cycle (default), 1 = Jacobi, 2 = multigrid W-cycle */
+    int32_t precond;       /* pressure preconditioner: 0 = multigrid V-cycle (default), 1 = Jacobi, 2 = multigrid W-cycle,
+                            * 3 = multigrid V-cycle in FP32 arithmetic (CG itself stays FP64) */
     int32_t sat_block;     /* transport: 0 = cluster kernel, all sub-steps of a step in one launch, where a member's tiles fit a cluster (default); 1 = one sub-step per launch */
     int32_t reserved;
 } hm_sim_desc;
