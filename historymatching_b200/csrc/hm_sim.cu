@@ -306,7 +306,7 @@ __device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uin
                  "l"(__double_as_longlong(v)), "r"(remote_bar) : "memory");
 }
 
-template <bool HAS_POR, int NT>
+template <bool HAS_POR, int NT, int CPT>
 __global__ void __launch_bounds__(NT, 1)
 k_sat_cluster(Geo g, Fluid fl, Wells w, int step, double dt, const int* __restrict__ nts,
               const double* __restrict__ Sin, double* __restrict__ Sout, const double* __restrict__ Vxl,
@@ -315,7 +315,7 @@ k_sat_cluster(Geo g, Fluid fl, Wells w, int step, double dt, const int* __restri
     extern __shared__ double smc[];  // fw[2][(R+2)*Ny] (halo row, R tile rows, halo row), src[R*Ny]
     __shared__ int wc[kMaxWells];
     __shared__ double wr[kMaxWells];
-    constexpr int CPT = kTileCells / NT;
+    constexpr int kCells = NT * CPT;  // cells of a full tile (the Geo passed in carries the matching R / nTiles)
     cg::cluster_group cluster = cg::this_cluster();
     const int m = blockIdx.x / g.nTiles, t = blockIdx.x % g.nTiles;  // t == rank in the cluster
     const int r0 = t * g.R, r1 = min(r0 + g.R, g.Nx), rows = r1 - r0;
@@ -403,7 +403,7 @@ k_sat_cluster(Geo g, Fluid fl, Wells w, int step, double dt, const int* __restri
         sendDn[j] = in && e >= nInt - Ny && hasDn;
         anyEdge = anyEdge || edge[j];
     }
-    const bool full = nInt == kTileCells;
+    const bool full = nInt == kCells;
     cluster.sync();  // tiles zeroed and mbarriers initialised in every CTA before remote traffic starts
     if (full && Ny <= NT && Ny % 32 == 0) {
         // Fast path (full tile, rows are whole warps): the first row lives in cell 0 of threads [0, Ny), the
@@ -639,15 +639,24 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
         HM_CUDA(cudaFuncSetAttribute(k_sat_substep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     }
     const int copy_blocks = (int)((vec + 255) / 256);
-    // transport: all sub-steps of a time step in one cluster launch when the member's tiles fit a cluster
-    const bool use_cluster = d.sat_block != 1 && g.nTiles <= 16;
-    const size_t smem_cluster = ((size_t)2 * (g.R + 2) * d.Ny + (size_t)g.R * d.Ny) * sizeof(double);
-    const int cluster_threads = d.sat_block == 2 ? 512 : 1024;
+    // transport: all sub-steps of a time step in one cluster launch when the member's tiles fit a cluster.
+    // Two tile shapes: 2048 cells (1024 threads x 2 cells, the default) and 4096 cells (512 threads x 8 cells:
+    // clusters of <= 4 CTAs place on all 148 SMs, but 16 warps per SM hide less latency - measured 25 % slower
+    // at 128^2).  sat_block: 0 / 2 = 2048-cell tiles, 1 = streaming kernel, 3 = 4096-cell tiles.
+    Geo gc = g;
+    bool big_tile = d.sat_block == 3 && 4096 / d.Ny >= 2;  // measured slower than 2048-cell tiles at 128^2
+    if (big_tile) {
+        gc.R = std::min(d.Nx, 4096 / d.Ny);
+        gc.nTiles = (d.Nx + gc.R - 1) / gc.R;
+    }
+    const bool use_cluster = d.sat_block != 1 && gc.nTiles <= 16;
+    const int cluster_threads = big_tile ? 512 : 1024;
+    const size_t smem_cluster = ((size_t)2 * (gc.R + 2) * d.Ny + (size_t)gc.R * d.Ny) * sizeof(double);
+    auto cluster_kernel = d.por ? (big_tile ? k_sat_cluster<true, 512, 8> : k_sat_cluster<true, 1024, 2>)
+                                : (big_tile ? k_sat_cluster<false, 512, 8> : k_sat_cluster<false, 1024, 2>);
     if (use_cluster) {
-        auto kern = d.por ? (cluster_threads == 1024 ? k_sat_cluster<true, 1024> : k_sat_cluster<true, 512>)
-                          : (cluster_threads == 1024 ? k_sat_cluster<false, 1024> : k_sat_cluster<false, 512>);
-        HM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cluster));
-        if (g.nTiles > 8) HM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        HM_CUDA(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cluster));
+        if (gc.nTiles > 8) HM_CUDA(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     }
 
     // initial state: S <- S0, P <- 0 (cold start of the first solve), flags
@@ -699,22 +708,20 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
         int sat_launches = 0;
         if (use_cluster) {
             cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3((unsigned)grid);
+            cfg.gridDim = dim3((unsigned)(nm * gc.nTiles));
             cfg.blockDim = dim3(cluster_threads);
             cfg.dynamicSmemBytes = smem_cluster;
             cfg.stream = st;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = (unsigned)g.nTiles;
+            attr[0].val.clusterDim.x = (unsigned)gc.nTiles;
             attr[0].val.clusterDim.y = 1;
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
             const double* porp = d.por;
-            auto kern = d.por ? (cluster_threads == 1024 ? k_sat_cluster<true, 1024> : k_sat_cluster<true, 512>)
-                              : (cluster_threads == 1024 ? k_sat_cluster<false, 1024> : k_sat_cluster<false, 512>);
-            HM_CUDA(cudaLaunchKernelEx(&cfg, kern, g, fl, w, step, d.dt, (const int*)nts, (const double*)Scur, Snxt,
-                                       (const double*)Vxl, (const double*)Vyl, porp));
+            HM_CUDA(cudaLaunchKernelEx(&cfg, cluster_kernel, gc, fl, w, step, d.dt, (const int*)nts, (const double*)Scur,
+                                       Snxt, (const double*)Vxl, (const double*)Vyl, porp));
             std::swap(Scur, Snxt);
             sat_launches = 1;
         } else {

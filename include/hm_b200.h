@@ -102,7 +102,9 @@ typedef struct hm_sim_desc {
     int32_t chunk_members; /* <=0: all members in one launch wave */
     int32_t precond;       /* pressure preconditioner: 0 = multigrid V-cycle (default), 1 = Jacobi, 2 = multigrid W-cycle,
                             * 3 = multigrid V-cycle in FP32 arithmetic (CG itself stays FP64) */
-    int32_t sat_block;     /* transport: 0 = cluster kernel, all sub-steps of a step in one launch, where a member's tiles fit a cluster (default); 1 = one sub-step per launch */
+    int32_t sat_block;     /* transport: 0 = cluster kernel (all sub-steps of a step in one launch) where a member's tiles fit a
+                            * cluster, tile shape chosen automatically; 1 = streaming kernel, one sub-step per launch;
+                            * 2 / 3 = cluster kernel with 2048- / 4096-cell tiles */
     int32_t reserved;
 } hm_sim_desc;
 
