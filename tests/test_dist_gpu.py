@@ -1,0 +1,72 @@
+"""world_size-2 NCCL test of the member-sharded analysis step (needs 2 GPUs; skipped otherwise).
+
+Every rank simulates its own block of members (no communication), then the ES update runs
+member-sharded: all_gather of the predicted data, all_to_all member rows -> parameter columns,
+update on the local columns, all_to_all back.  The result must equal the
+single-device update of the full ensemble (same CUDA kernels, columns are independent).
+"""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, size, port, out):
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=size, device_id=dev)
+    from historymatching_b200 import analysis as ha
+    from historymatching_b200 import dist as hd
+    from historymatching_b200.workflow import HistoryMatchCase
+
+    case = HistoryMatchCase(20, 20, 2.0, 1.0, 0.025, 6)
+    N, M, p = 13, case.grid.M, case.p  # uneven member blocks (7 + 6), uneven column blocks
+    rng = np.random.RandomState(3)  # same stream on every rank
+    E = torch.as_tensor(np.clip(rng.randn(N, M), -2, 2) * 0.3, device=dev)
+    obs = torch.as_tensor(rng.rand(p) * 0.3, device=dev)
+    Z = torch.as_tensor(rng.randn(N, p), device=dev)
+    pert = Z @ torch.as_tensor(case.R12.T.copy(), device=dev)
+    dec = torch.as_tensor(case.decorr, device=dev)
+    taper = torch.as_tensor(rng.rand(M, p), device=dev)
+    lo, hi = hd.member_slice(N)
+    clo, chi = hd.column_slice(M)
+
+    Eo_loc, res = case.forward(E[lo:hi].contiguous())
+    assert not res.status.any()
+    Eo_full, _ = case.forward(E)  # reference: the whole ensemble on this device
+    ok = torch.equal(hd.gather_members(Eo_loc, N), Eo_full)  # members are independent: bit-identical
+
+    post = hd.sharded_update(ha.ens_update0, E[lo:hi].contiguous(), Eo_loc, N, obs=obs, perturbs=pert, decorr=dec)
+    ref = ha.ens_update0(E, Eo_full, obs=obs, perturbs=pert, decorr=dec)
+    ok = ok and torch.allclose(post, ref[lo:hi], rtol=1e-10, atol=1e-12)
+    post_loc = hd.sharded_update(ha.ens_update0_loc, E[lo:hi].contiguous(), Eo_loc, N, obs=obs, perturbs=pert,
+                                 decorr=dec, taper=taper[clo:chi].contiguous())
+    ref_loc = ha.ens_update0_loc(E, Eo_full, obs=obs, perturbs=pert, decorr=dec, taper=taper)
+    ok = ok and torch.allclose(post_loc, ref_loc[lo:hi], rtol=1e-10, atol=1e-12)
+    with open(os.path.join(out, f"rank{rank}"), "w") as f:
+        f.write(str(int(ok)))
+    dist.destroy_process_group()
+
+
+def test_sharded_forward_and_update_world2_nccl(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert [open(tmp_path / f"rank{r}").read() for r in range(2)] == ["1", "1"]
