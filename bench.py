@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--ntime", type=int, default=0, help="override simulator steps per pass (development)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-update-bench", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the baseline sample")
     ap.add_argument("--sat-block", type=int, default=0, help="transport kernel variant (hm_sim_desc.sat_block)")
     ap.add_argument("--precond", type=int, default=0, help="pressure preconditioner (hm_sim_desc.precond)")
@@ -150,6 +151,82 @@ def run_reference(args, wl, rank):
                 cpu_baseline=dict(value=value, unit="member*steps/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=value, unit="member*steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
+
+
+# ---- update wall times + FP64 GEMM roofline (second half of the BASELINE metric) -----------------------
+def update_benchmarks(case, E0, Eo, noisy, pert, dec, cpu=True, reps=5):
+    """ES / LES / IES-iteration wall times at the bench ensemble size (CUDA events, inputs resident) and the
+    FP64 tensor-core GEMM of the IES recomposition E = x0 + W X0 against a cuBLAS DGEMM timed in the same run."""
+    import ctypes as C
+
+    import torch
+
+    from historymatching_b200 import _lib
+    from historymatching_b200 import analysis as ha
+
+    dev = E0.device
+    N, M = E0.shape
+    p = Eo.shape[1]
+    ctx = _lib.Context.get(dev.index or 0)
+    ctx.use_torch_stream()
+
+    def timed(fn, n=reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    out = dict(N=N, M=M, p=p)
+    out["es_ms"] = timed(lambda: ha.ens_update0(E0, Eo, noisy, pert, dec))
+    # localised ES: bump taper of radius 1.2 between cell centres and the (well, time) observations (HM:863)
+    g = case.grid
+    ix, iy = np.divmod(np.arange(M), g.Ny)
+    xy_prm = np.stack([(ix + 0.5) * g.Lx / g.Nx, (iy + 0.5) * g.Ly / g.Ny], 1)
+    xy_obs = np.tile(xy_prm[case.obs_cell], (case.nTime, 1))
+    taper = ha.bump_taper(torch.as_tensor(xy_prm, device=dev), torch.as_tensor(xy_obs, device=dev), 1.2)
+    out["les_ms"] = timed(lambda: ha.ens_update0_loc(E0, Eo, noisy, pert, dec, taper), n=2)
+    # one IES iteration of algebra: hm_ies_step (N x N solve) + recomposition GEMM (HM:920-944)
+    W = torch.eye(N, dtype=torch.float64, device=dev)
+    X0 = E0 - E0.mean(0, keepdim=True)
+    x0 = E0.mean(0)
+
+    def ies_iter():
+        _lib.check(ctx.lib.hm_ies_step(ctx.handle, N, p, C.c_void_p(W.data_ptr()), C.c_void_p(Eo.data_ptr()),
+                                       C.c_void_p(noisy.data_ptr()), C.c_void_p(pert.data_ptr()),
+                                       C.c_void_p(dec.data_ptr()), 0.4))
+        return ha._recompose(ctx, x0, W, X0)
+
+    out["ies_iter_ms"] = timed(ies_iter)
+    # FP64 GEMM roofline: the recomposition product W (N x N) @ X0 (N x M), 2 N^2 M flops
+    Cm = torch.empty_like(X0)
+
+    def gemm():
+        _lib.check(ctx.lib.hm_dgemm(ctx.handle, 0, 0, N, M, N, 1.0, C.c_void_p(W.data_ptr()), N,
+                                    C.c_void_p(X0.data_ptr()), M, 0.0, C.c_void_p(Cm.data_ptr()), M))
+
+    ms = timed(gemm)
+    A = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+    ms_peak = timed(lambda: torch.matmul(A, A), n=3)
+    ms_same = timed(lambda: torch.matmul(W, X0))
+    peak = 2 * 4096**3 / ms_peak / 1e9
+    ach = 2.0 * N * N * M / ms / 1e9
+    out["dgemm"] = dict(kernel="k_dgemm (mma.sync m8n8k4 f64, DMMA) W@X0 %dx%dx%d" % (N, M, N), bound="tensor",
+                        achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak,
+                        peak_source="cuBLAS DGEMM 4096^3 timed in this run",
+                        cublas_same_shape=2.0 * N * N * M / ms_same / 1e9)
+    if cpu:  # the reference's numpy path (oracle, pinned to the reference's own functions by the golden vectors)
+        from oracle import analysis as oa
+
+        En, Eon, yn, pn, dn = (x.cpu().numpy() for x in (E0, Eo, noisy, pert, dec))
+        t0 = time.perf_counter()
+        oa.ens_update0(En, Eon, yn, pn, dn)
+        out["es_cpu_ms"] = 1e3 * (time.perf_counter() - t0)
+    return out
 
 
 # ---- GPU arm ------------------------------------------------------------------------------------
@@ -339,6 +416,8 @@ def main():
     )
     if e2e:
         line["e2e"] = e2e
+    if world == 1 and not args.no_update_bench:
+        line["update"] = update_benchmarks(case, E0, Eo, noisy, pert, dec, cpu=not args.no_cpu_baseline)
     if not args.no_cpu_baseline and world == 1:
         v, cores, sample = cpu_forward_sample(wl, args.cpu_seconds)
         line["cpu_baseline"] = dict(value=v, unit="member*steps/s", cores=cores, kind="port", sample=sample)

@@ -16,8 +16,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhm_b200.so")
-SOURCES = ["hm_api.cu", "hm_sim.cu", "hm_pressure.cu", "hm_gemm.cu", "hm_analysis.cu"]
+SOURCES = ["hm_api.cu", "hm_sim.cu", "hm_pressure.cu", "hm_small.cu", "hm_gemm.cu", "hm_analysis.cu"]
 HEADERS = [os.path.join(CSRC, "hm_common.cuh"), os.path.join(CSRC, "hm_sim_common.cuh"),
+           os.path.join(CSRC, "hm_mg_onchip.cuh"),
            os.path.join(HERE, "..", "include", "hm_b200.h")]
 
 

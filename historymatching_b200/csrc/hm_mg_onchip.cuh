@@ -1,0 +1,209 @@
+// Multigrid hierarchy resident in shared memory: device functions shared by
+//   * k_mg_onchip (hm_pressure.cu): the coarse levels (<= 4096 cells) of the streamed solver, and
+//   * k_sim_small (hm_small.cu): the whole simulator of a small grid in one CTA.
+// A CTA of NT threads owns one member; a thread handles up to PER cells of a level
+// (cell e = tid + k*NT).  Every control variable is CTA-uniform.
+#pragma once
+
+#include "hm_sim_common.cuh"
+
+namespace hmsim {
+
+constexpr int kMaxLevels = 14;
+constexpr int kWcycleMinCells = 64;  // recurse twice into a coarse level with at least this many cells
+// NU Jacobi sweeps weighted by the reciprocal roots of the degree-NU Chebyshev polynomial on
+// [2/8, 2] (the spectrum of D^-1 A lies in [0, 2]): same cost as damped Jacobi, markedly better
+// smoothing.  Pre-smoothing applies the weights in order, post-smoothing in reverse order, which
+// keeps the cycle symmetric (the smoother is a polynomial in D^-1 A either way).
+#ifndef HM_NU
+#define HM_NU 3
+#endif
+constexpr int kNu = HM_NU;
+__device__ __forceinline__ double cheb_w(int i) {
+    if (kNu == 2)  // interval [1/3, 2]
+        return i == 0 ? 1.0 / 1.7559223176554566 : 1.0 / 0.57741101567787674;
+    if (kNu == 3)  // interval [1/4, 2]: 1 / (1.125 + 0.875 cos(pi (2i+1) / 6))
+        return i == 0 ? 1.0 / 1.8827722283113838 : i == 1 ? 1.0 / 1.125 : 1.0 / 0.36722777168861618;
+    // kNu == 4, interval [1/5, 2]: 1 / (1.1 + 0.9 cos(pi (2i+1) / 8))
+    return i == 0 ? 1.0 / 1.9314915792601581 : i == 1 ? 1.0 / 1.4444150891285809
+         : i == 2 ? 1.0 / 0.75558491087141922 : 1.0 / 0.26850842073984186;
+}
+
+struct OnchipMeta {
+    int n;                  // number of on-chip levels
+    int nx[kMaxLevels], ny[kMaxLevels], M[kMaxLevels], off[kMaxLevels];
+    float inv_ny[kMaxLevels];
+    const void* TX[kMaxLevels];
+    const void* TY[kMaxLevels];
+    const void* dinv[kMaxLevels];
+    int total;              // total cells over the on-chip levels
+    int wmin;               // W-cycle: visit a coarse level twice if it has >= wmin cells (V-cycle: INT_MAX)
+};
+
+// X: iterate, B: right-hand side, TX / TY: low-face transmissibilities, DV: 1 / diagonal; all levels back to
+// back, level l at offset mt.off[l]
+template <typename T>
+struct OnchipSmem {
+    T *X, *B, *TX, *TY, *DV;
+};
+
+__device__ __forceinline__ void cell_ij(int e, int ny, float inv_ny, int& i, int& j) {
+    i = __float2int_rd(((float)e + 0.5f) * inv_ny);  // exact for e < 2^22
+    j = e - i * ny;
+}
+
+template <typename T>
+__device__ __forceinline__ T onchip_Ax(const OnchipMeta& mt, const OnchipSmem<T>& s, int l, int e, int i, int j,
+                                       T pin) {
+    const int ny = mt.ny[l], o = mt.off[l] + e;
+    const T xc = s.X[o];
+    T y = 0;
+    if (i > 0) y = s.TX[o] * (xc - s.X[o - ny]);
+    if (i < mt.nx[l] - 1) y = fma(s.TX[o + ny], xc - s.X[o + ny], y);
+    if (j > 0) y = fma(s.TY[o], xc - s.X[o - 1], y);
+    if (j < ny - 1) y = fma(s.TY[o + 1], xc - s.X[o + 1], y);
+    if (e == 0) y = fma(pin, xc, y);
+    return y;
+}
+
+// nsweep weighted-Jacobi sweeps on level l, in place (new values staged in registers)
+template <typename T, int NT, int PER>
+__device__ __forceinline__ void onchip_smooth(const OnchipMeta& mt, const OnchipSmem<T>& s, int l, T pin,
+                                              int nsweep, bool reverse) {
+    const int M = mt.M[l], ny = mt.ny[l], o = mt.off[l];
+    const float inv = mt.inv_ny[l];
+    for (int sw = 0; sw < nsweep; ++sw) {
+        const T wgt = (T)cheb_w(reverse ? (kNu - 1 - sw % kNu) : sw % kNu);
+        T xn[PER];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int e = threadIdx.x + k * NT;
+            if (e < M) {
+                int i, j;
+                cell_ij(e, ny, inv, i, j);
+                xn[k] = s.X[o + e] + wgt * s.DV[o + e] * (s.B[o + e] - onchip_Ax<T>(mt, s, l, e, i, j, pin));
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int e = threadIdx.x + k * NT;
+            if (e < M) s.X[o + e] = xn[k];
+        }
+        __syncthreads();
+    }
+}
+
+// Residual of level l restricted to level l+1 (each coarse thread evaluates its own children);
+// the coarse iterate is reset to zero.
+template <typename T, int NT>
+__device__ __forceinline__ void onchip_restrict(const OnchipMeta& mt, const OnchipSmem<T>& s, int l, T pin) {
+    const int ny = mt.ny[l], nx = mt.nx[l], o = mt.off[l];
+    const int cM = mt.M[l + 1], cny = mt.ny[l + 1], co = mt.off[l + 1];
+    const float cinv = mt.inv_ny[l + 1];
+    for (int e = threadIdx.x; e < cM; e += NT) {
+        int ci, cj;
+        cell_ij(e, cny, cinv, ci, cj);
+        T r = 0;
+#pragma unroll
+        for (int di = 0; di < 2; ++di)
+#pragma unroll
+            for (int dj = 0; dj < 2; ++dj) {
+                const int i = 2 * ci + di, j = 2 * cj + dj;
+                if (i < nx && j < ny) {
+                    const int fe = i * ny + j;
+                    r += s.B[o + fe] - onchip_Ax<T>(mt, s, l, fe, i, j, pin);
+                }
+            }
+        s.B[co + e] = r;
+        s.X[co + e] = 0;
+    }
+    __syncthreads();
+}
+
+template <typename T, int NT>
+__device__ __forceinline__ void onchip_prolong(const OnchipMeta& mt, const OnchipSmem<T>& s, int l) {
+    const int M = mt.M[l], ny = mt.ny[l], o = mt.off[l], cny = mt.ny[l + 1], co = mt.off[l + 1];
+    const float inv = mt.inv_ny[l];
+    for (int e = threadIdx.x; e < M; e += NT) {
+        int i, j;
+        cell_ij(e, ny, inv, i, j);
+        s.X[o + e] += s.X[co + (i >> 1) * cny + (j >> 1)];
+    }
+    __syncthreads();
+}
+
+// Coarse operators of level l+1 from level l (2x2 aggregation, piecewise-constant transfer, Galerkin / 2:
+// coarse T = half the sum of the fine T crossing the coarse face); same arithmetic as k_mg_coarsen.
+template <typename T, int NT>
+__device__ __forceinline__ void onchip_coarsen(const OnchipMeta& mt, const OnchipSmem<T>& s, int l, T pin) {
+    const int fnx = mt.nx[l], fny = mt.ny[l], fo = mt.off[l];
+    const int cM = mt.M[l + 1], cny = mt.ny[l + 1], co = mt.off[l + 1];
+    const float cinv = mt.inv_ny[l + 1];
+    const T* TX = s.TX + fo;
+    const T* TY = s.TY + fo;
+    for (int e = threadIdx.x; e < cM; e += NT) {
+        int I, J;
+        cell_ij(e, cny, cinv, I, J);
+        const int fi = 2 * I, fj = 2 * J;
+        const bool j1 = fj + 1 < fny, i1 = fi + 1 < fnx;
+        auto tx = [&](int i) {
+            if (i >= fnx) return (T)0;
+            return (T)0.5 * (TX[i * fny + fj] + (j1 ? TX[i * fny + fj + 1] : (T)0));
+        };
+        auto ty = [&](int j) {
+            if (j >= fny) return (T)0;
+            return (T)0.5 * (TY[fi * fny + j] + (i1 ? TY[(fi + 1) * fny + j] : (T)0));
+        };
+        const T txl = tx(fi), txh = tx(fi + 2), tyl = ty(fj), tyh = ty(fj + 2);
+        T d = tyl + tyh + txl + txh;
+        if (e == 0) d += pin;
+        s.TX[co + e] = txl;
+        s.TY[co + e] = tyl;
+        s.DV[co + e] = (T)1 / d;
+    }
+    __syncthreads();
+}
+
+// One multigrid cycle on the shared-memory hierarchy: X[level 0] = M^-1 B[level 0] (zero initial guess).
+// The cycle (V, or W on the levels of at least `wmin` cells) is an explicit state machine: `left` packs,
+// 4 bits per level, how many cycles are still to be run on that level.
+template <typename T, int NT, int PER>
+__device__ __forceinline__ void onchip_cycle(const OnchipMeta& mt, const OnchipSmem<T>& s, T pinv) {
+    const int M0 = mt.M[0];
+    unsigned long long left = (M0 >= mt.wmin) ? 2ull : 1ull;
+    int l = 0;
+    bool descend = true;
+    while (true) {
+        if (descend) {  // start a cycle on level l
+            if (l == mt.n - 1) {
+                if (mt.M[l] == 1) {
+                    if (threadIdx.x == 0) s.X[mt.off[l]] = s.B[mt.off[l]] * s.DV[mt.off[l]];
+                    __syncthreads();
+                } else {
+                    onchip_smooth<T, NT, PER>(mt, s, l, pinv, 3 * kNu, false);
+                }
+                left -= 1ull << (4 * l);
+                descend = false;
+            } else {
+                onchip_smooth<T, NT, PER>(mt, s, l, pinv, kNu, false);
+                onchip_restrict<T, NT>(mt, s, l, pinv);
+                ++l;
+                left |= ((mt.M[l] >= mt.wmin) ? 2ull : 1ull) << (4 * l);
+            }
+        } else {  // a cycle on level l has just finished
+            if ((left >> (4 * l)) & 15ull) {
+                descend = true;
+            } else if (l == 0) {
+                break;
+            } else {
+                --l;
+                onchip_prolong<T, NT>(mt, s, l);
+                onchip_smooth<T, NT, PER>(mt, s, l, pinv, kNu, true);
+                left -= 1ull << (4 * l);
+            }
+        }
+    }
+}
+
+}  // namespace hmsim

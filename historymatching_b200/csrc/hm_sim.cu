@@ -21,6 +21,8 @@
 //   k_sat_substep  read S,Vxl,Vyl      write S'                  32 B / sub-step
 #include <cooperative_groups.h>
 
+#include <type_traits>
+
 #include "hm_sim_common.cuh"
 
 using namespace hmsim;
@@ -30,6 +32,8 @@ int pressure_solve(hm_ctx* ctx, const Geo& g, const Wells& w, int step, int nm, 
                    const double* TYl, const double* dinv, const double* pin, double* P, double rtol,
                    int max_iter, int precond, int* done, int* iters, int* counters, int* cg_batch,
                    int* iters_used, bool* all_done_out);
+int sim_small_supported(const hm_sim_desc& d);
+int sim_small(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm);
 }
 
 namespace {
@@ -143,28 +147,6 @@ __global__ void k_substep_count(Geo g, int n_members, double dt, const double* _
 // shared memory and then applies the upwind stencil.  Wells touch a handful of cells and are
 // applied as a fix-up pass after the sweep (the source terms are additive in the update).
 constexpr int kSatCPT = kTileCells / kThreads;
-
-struct Fluid {
-    double inv_range;  // 1 / (1 - swc - sor)
-    double swc_ir;     // swc / (1 - swc - sor)
-    double mr;         // mobility ratio vw / vo:  fw = se^2 / (se^2 + mr (1-se)^2)
-};
-// a / b for b well inside the float range: MUFU.RCP seed (2^-23), one Newton step (2^-46) and a
-// residual correction of the quotient; agrees with IEEE division to <= 1 ulp, no branches.
-__device__ __forceinline__ double fast_div(double a, double b) {
-    float r32;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r32) : "f"((float)b));
-    double r = (double)r32;
-    r = fma(r, fma(-b, r, 1.0), r);
-    const double q = a * r;
-    return fma(fma(-b, q, a), r, q);
-}
-__device__ __forceinline__ double frac_flow_fast(double s, const Fluid& f) {
-    const double se = fma(s, f.inv_range, -f.swc_ir);
-    const double t = 1.0 - se;
-    const double a = se * se;
-    return fast_div(a, fma(f.mr * t, t, a));  // denominator >= min(1, mr)/2 > 0 for every saturation
-}
 
 // The flux arrays carry a zero pad (Ny resp. 1 elements) behind the last member, and the low
 // faces of row 0 / column 0 are zero by construction, so the HIGH faces of the last row /
@@ -306,7 +288,7 @@ __device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uin
                  "l"(__double_as_longlong(v)), "r"(remote_bar) : "memory");
 }
 
-template <bool HAS_POR, int NT, int CPT>
+template <bool HAS_POR, int NT, int CPT, int NY>
 __global__ void __launch_bounds__(NT, 1)
 k_sat_cluster(Geo g, Fluid fl, Wells w, int step, double dt, const int* __restrict__ nts,
               const double* __restrict__ Sin, double* __restrict__ Sout, const double* __restrict__ Vxl,
@@ -319,7 +301,8 @@ k_sat_cluster(Geo g, Fluid fl, Wells w, int step, double dt, const int* __restri
     cg::cluster_group cluster = cg::this_cluster();
     const int m = blockIdx.x / g.nTiles, t = blockIdx.x % g.nTiles;  // t == rank in the cluster
     const int r0 = t * g.R, r1 = min(r0 + g.R, g.Nx), rows = r1 - r0;
-    const int Ny = g.Ny, nInt = rows * Ny, fwLen = (g.R + 2) * Ny;
+    const int Ny = NY ? NY : g.Ny;  // NY != 0: row length known at compile time (immediate shared-memory offsets)
+    const int nInt = rows * Ny, fwLen = (g.R + 2) * Ny;
     const int64_t base = (int64_t)m * g.M + (int64_t)r0 * Ny;
     const int n = nts[m];
     double* const fwb0 = smc;
@@ -343,10 +326,18 @@ k_sat_cluster(Geo g, Fluid fl, Wells w, int step, double dt, const int* __restri
     }
     __syncthreads();
 
+    // Cell -> thread map.  Fast path (full tile, rows are whole warps, NT a multiple of Ny): thread (q, col)
+    // owns the CPT consecutive grid rows q*CPT .. q*CPT+CPT-1 at column col, so that the x-neighbours inside the
+    // row group are the thread's own registers (2 + 2 CPT shared-memory loads per sub-step instead of 4 CPT).
+    // General path: cell e = tid + j*NT.
+    const bool full = nInt == kCells;
+    const bool fast = full && NT % Ny == 0 && Ny % 32 == 0;
+    const int q = fast ? threadIdx.x / Ny : 0, col = fast ? threadIdx.x - q * Ny : 0;
+    const int e0 = fast ? q * CPT * Ny + col : threadIdx.x, es = fast ? Ny : NT;
     double s[CPT], aW[CPT], aS[CPT], aN[CPT], aE[CPT], dg[CPT], sr[CPT];
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
-        const int e = threadIdx.x + j * NT;
+        const int e = e0 + j * es;
         s[j] = aW[j] = aS[j] = aN[j] = aE[j] = dg[j] = sr[j] = 0.0;
         if (e < nInt) {
             const int64_t gc = base + e;
@@ -359,10 +350,10 @@ k_sat_cluster(Geo g, Fluid fl, Wells w, int step, double dt, const int* __restri
             aS[j] = hdt * (vyl + fabs(vyl));
             aN[j] = hdt * (fabs(vyh) - vyh);
             aE[j] = hdt * (fabs(vxh) - vxh);
-            const double q = srcs[e];
+            const double qs = srcs[e];
             dg[j] = hdt * (((vyl - vyh) + (vxl - vxh)) - ((fabs(vyl) + fabs(vyh)) + (fabs(vxl) + fabs(vxh)))) +
-                    fmin(q, 0.0);
-            sr[j] = fmax(q, 0.0);
+                    fmin(qs, 0.0);
+            sr[j] = fmax(qs, 0.0);
         }
     }
     // remote halo rows: my first row is the high halo of tile t-1, my last row the low halo of tile t+1
@@ -403,39 +394,71 @@ k_sat_cluster(Geo g, Fluid fl, Wells w, int step, double dt, const int* __restri
         sendDn[j] = in && e >= nInt - Ny && hasDn;
         anyEdge = anyEdge || edge[j];
     }
-    const bool full = nInt == kCells;
     cluster.sync();  // tiles zeroed and mbarriers initialised in every CTA before remote traffic starts
-    if (full && Ny <= NT && Ny % 32 == 0) {
-        // Fast path (full tile, rows are whole warps): the first row lives in cell 0 of threads [0, Ny), the
-        // last row in cell CPT-1 of threads [NT-Ny, NT); no per-cell predicates in the loop.
-        const bool sUp = hasUp && threadIdx.x < Ny, sDn = hasDn && threadIdx.x >= NT - Ny;
+    if (fast) {
+        // No per-cell predicates in the loop.  The first tile row is cell 0 of the threads of row group 0, the
+        // last tile row cell CPT-1 of the last row group: exactly the threads that read the halo rows the
+        // neighbours fill, so "readers of a halo row == senders of the matching edge row" and a neighbour can
+        // never run more than one sub-step ahead of any reader (the fw tiles are double buffered).
+        const bool sUp = hasUp && q == 0, sDn = hasDn && q == NT / Ny - 1;
         const bool needWait = sUp || sDn;
-        for (int sub = 0; sub < n; ++sub) {
-            const bool odd = sub & 1;
-            double* fw = (odd ? fwb1 : fwb0) + Ny + threadIdx.x;
-            const uint32_t mybar = odd ? bar1 : bar0;
-            if (threadIdx.x == 0 && nNbr) mbar_expect_tx(mybar, nNbr * Ny * 8);
+        const uint32_t colb = 8u * (uint32_t)col;
+        const bool unit = fl.inv_range == 1.0 && fl.swc_ir == 0.0 && fl.mr == 1.0;
+        const bool lead = threadIdx.x < 32;  // warp-uniform: only warp 0 runs the expect_tx branch
+        auto substep = [&](auto unit_tag, double* __restrict__ fw, uint32_t mybar, uint32_t upA, uint32_t upB,
+                           uint32_t dnA, uint32_t dnB, int parity) {
+            constexpr bool U = decltype(unit_tag)::value;
+            if (lead) {
+                if (threadIdx.x == 0 && nNbr) mbar_expect_tx(mybar, nNbr * Ny * 8);
+            }
             double f[CPT];
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
-                f[j] = frac_flow_fast(s[j], fl);
-                fw[j * NT] = f[j];
+                f[j] = frac_flow_loop<U>(s[j], fl);
+                fw[j * Ny] = f[j];
             }
-            if (sUp) st_async_f64((odd ? up1 : up0) + 8u * threadIdx.x, f[0], odd ? upb1 : upb0);
-            if (sDn) st_async_f64((odd ? dn1 : dn0) + 8u * (threadIdx.x - (NT - Ny)), f[CPT - 1], odd ? dnb1 : dnb0);
-            __syncthreads();
-            if (needWait) mbar_wait(mybar, (sub >> 1) & 1);
+            if (sUp) st_async_f64(upA + colb, f[0], upB);
+            if (sDn) st_async_f64(dnA + colb, f[CPT - 1], dnB);
+            double acc[CPT];  // the terms that only need this thread's registers, before the barrier
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
-                const double* fp = fw + j * NT;
-                double acc = aW[j] * fp[-Ny];
-                acc = fma(aS[j], fp[-1], acc);
-                acc = fma(dg[j], f[j], acc);
-                acc = fma(aN[j], fp[1], acc);
-                acc = fma(aE[j], fp[Ny], acc);
-                s[j] += acc + sr[j];
+                acc[j] = fma(dg[j], f[j], sr[j]);
+                if (j > 0) acc[j] = fma(aW[j], f[j - 1], acc[j]);
+                if (j < CPT - 1) acc[j] = fma(aE[j], f[j + 1], acc[j]);
             }
-        }
+            __syncthreads();
+            if (needWait) mbar_wait(mybar, parity);
+            double fS[CPT], fN[CPT];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                fS[j] = fw[j * Ny - 1];
+                fN[j] = fw[j * Ny + 1];
+            }
+            const double fWest = fw[-Ny], fEast = fw[CPT * Ny];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                double a2 = fma(aS[j], fS[j], acc[j]);
+                a2 = fma(aN[j], fN[j], a2);
+                if (j == 0) a2 = fma(aW[j], fWest, a2);
+                if (j == CPT - 1) a2 = fma(aE[j], fEast, a2);
+                s[j] += a2;
+            }
+        };
+        double* const fwa = fwb0 + Ny + e0;
+        double* const fwb = fwb1 + Ny + e0;
+        auto run = [&](auto unit_tag) {
+            int sub = 0;
+            for (; sub + 1 < n; sub += 2) {
+                const int par = (sub >> 1) & 1;
+                substep(unit_tag, fwa, bar0, up0, upb0, dn0, dnb0, par);
+                substep(unit_tag, fwb, bar1, up1, upb1, dn1, dnb1, par);
+            }
+            if (sub < n) substep(unit_tag, fwa, bar0, up0, upb0, dn0, dnb0, (sub >> 1) & 1);
+        };
+        if (unit)
+            run(std::true_type{});
+        else
+            run(std::false_type{});
     } else
     for (int sub = 0; sub < n; ++sub) {
         const bool odd = sub & 1;
@@ -483,7 +506,7 @@ k_sat_cluster(Geo g, Fluid fl, Wells w, int step, double dt, const int* __restri
     }
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
-        const int e = threadIdx.x + j * NT;
+        const int e = e0 + j * es;
         if (e < nInt) Sout[base + e] = s[j];
     }
     cluster.sync();  // no CTA may exit while a neighbour can still write into its shared memory
@@ -529,6 +552,16 @@ __global__ void k_extrapolate(int64_t n, double* __restrict__ P, double* __restr
     P[i] = 2.0 * p - Pprev[i];
     Pprev[i] = p;
 }
+// quadratic extrapolation from three time levels: P <- 3 P - 3 Pprev + Pprev2, shifting the history
+__global__ void k_extrapolate2(int64_t n, double* __restrict__ P, double* __restrict__ Pprev,
+                               double* __restrict__ Pprev2) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double p1 = P[i], p2 = Pprev[i], p3 = Pprev2[i];
+    P[i] = 3.0 * (p1 - p2) + p3;
+    Pprev2[i] = p2;
+    Pprev[i] = p1;
+}
 
 __global__ void k_mark_unconverged(int n_members, const int* __restrict__ done, int* __restrict__ cg_fail) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -565,6 +598,7 @@ struct PhaseTimer {
 };
 
 int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
+    if (sim_small_supported(d)) return sim_small(ctx, d, m0, nm);  // whole simulator in one kernel (hm_small.cu)
     cudaStream_t st = ctx->stream;
     Geo g;
     g.Nx = d.Nx;
@@ -598,6 +632,8 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
     HM_CHECK(ctx->ws.get("sim.P", vec, &P));
     double* Pprev;
     HM_CHECK(ctx->ws.get("sim.Pprev", vec, &Pprev));
+    double* Pprev2 = nullptr;
+    if (d.warm_start == 2) HM_CHECK(ctx->ws.get("sim.Pprev2", vec, &Pprev2));
     HM_CHECK(ctx->ws.get("sim.Vxl", vec + (size_t)d.Ny, &Vxl));  // + zero pad, see sat_tile_body
     HM_CHECK(ctx->ws.get("sim.Vyl", vec + 1, &Vyl));
     HM_CHECK(ctx->ws.get("sim.Sa", vec, &Sa));
@@ -639,21 +675,17 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
         HM_CUDA(cudaFuncSetAttribute(k_sat_substep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     }
     const int copy_blocks = (int)((vec + 255) / 256);
-    // transport: all sub-steps of a time step in one cluster launch when the member's tiles fit a cluster.
-    // Two tile shapes: 2048 cells (1024 threads x 2 cells, the default) and 4096 cells (512 threads x 8 cells:
-    // clusters of <= 4 CTAs place on all 148 SMs, but 16 warps per SM hide less latency - measured 25 % slower
-    // at 128^2).  sat_block: 0 / 2 = 2048-cell tiles, 1 = streaming kernel, 3 = 4096-cell tiles.
-    Geo gc = g;
-    bool big_tile = d.sat_block == 3 && 4096 / d.Ny >= 2;  // measured slower than 2048-cell tiles at 128^2
-    if (big_tile) {
-        gc.R = std::min(d.Nx, 4096 / d.Ny);
-        gc.nTiles = (d.Nx + gc.R - 1) / gc.R;
-    }
+    // transport: all sub-steps of a time step in one cluster launch when the member's tiles fit a cluster
+    // (sat_block != 1).  Tile = 2048 cells = 1024 threads x 2 cells; measured alternatives at 128^2 x 1024 members:
+    // 512 threads x 4 cells the same speed, 4096-cell tiles (512 x 8, clusters of 4) spill and are 25 % slower.
+    // Row length 128 / 64 is a compile-time constant (immediate shared-memory offsets), other lengths are runtime.
+    const Geo gc = g;
     const bool use_cluster = d.sat_block != 1 && gc.nTiles <= 16;
-    const int cluster_threads = big_tile ? 512 : 1024;
+    const int cluster_threads = 1024;
     const size_t smem_cluster = ((size_t)2 * (gc.R + 2) * d.Ny + (size_t)gc.R * d.Ny) * sizeof(double);
-    auto cluster_kernel = d.por ? (big_tile ? k_sat_cluster<true, 512, 8> : k_sat_cluster<true, 1024, 2>)
-                                : (big_tile ? k_sat_cluster<false, 512, 8> : k_sat_cluster<false, 1024, 2>);
+    auto cluster_kernel = d.por ? k_sat_cluster<true, 1024, 2, 0> : k_sat_cluster<false, 1024, 2, 0>;
+    if (d.Ny == 128) cluster_kernel = d.por ? k_sat_cluster<true, 1024, 2, 128> : k_sat_cluster<false, 1024, 2, 128>;
+    if (d.Ny == 64) cluster_kernel = d.por ? k_sat_cluster<true, 1024, 2, 64> : k_sat_cluster<false, 1024, 2, 64>;
     if (use_cluster) {
         HM_CUDA(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cluster));
         if (gc.nTiles > 8) HM_CUDA(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -681,7 +713,11 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
                                                      TYl, dinv, pin);
         timer.mark(1);
         HM_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(int), st));
-        if (step >= 2 && d.reserved != 1) {  // P holds P_{k-1}, Pprev holds P_{k-2}
+        if (step >= 3 && d.warm_start == 2) {  // P = P_{k-1}, Pprev = P_{k-2}, Pprev2 = P_{k-3}
+            k_extrapolate2<<<copy_blocks, 256, 0, st>>>((int64_t)vec, P, Pprev, Pprev2);
+            ctx->sim_stats.kernel_launches += 1;
+        } else if (step >= 2 && d.warm_start != 1) {  // P holds P_{k-1}, Pprev holds P_{k-2}
+            if (d.warm_start == 2) HM_CUDA(cudaMemcpyAsync(Pprev2, Pprev, vec * sizeof(double), cudaMemcpyDeviceToDevice, st));
             k_extrapolate<<<copy_blocks, 256, 0, st>>>((int64_t)vec, P, Pprev);
             ctx->sim_stats.kernel_launches += 1;
         } else if (step == 1) {

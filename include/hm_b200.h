@@ -102,10 +102,13 @@ typedef struct hm_sim_desc {
     int32_t chunk_members; /* <=0: all members in one launch wave */
     int32_t precond;       /* pressure preconditioner: 0 = multigrid V-cycle (default), 1 = Jacobi, 2 = multigrid W-cycle,
                             * 3 = multigrid V-cycle in FP32 arithmetic (CG itself stays FP64) */
-    int32_t sat_block;     /* transport: 0 = cluster kernel (all sub-steps of a step in one launch) where a member's tiles fit a
-                            * cluster, tile shape chosen automatically; 1 = streaming kernel, one sub-step per launch;
-                            * 2 / 3 = cluster kernel with 2048- / 4096-cell tiles */
-    int32_t reserved;
+    int32_t sat_block;     /* kernel selection.  0 = automatic: grids of <= 2048 cells run the whole simulator in ONE kernel,
+                            * one CTA per member (hm_small.cu); larger grids take the streamed path with the cluster
+                            * transport kernel (all sub-steps of a time step in one launch) where a member's tiles fit a
+                            * thread-block cluster, else the streaming transport kernel.  1 = streamed path, streaming
+                            * transport kernel (one sub-step per launch).  2 = streamed path, cluster transport kernel. */
+    int32_t warm_start;    /* initial guess of a pressure solve from the previous time levels: 0 = linear extrapolation
+                            * (default), 1 = previous pressure, 2 = quadratic extrapolation */
 } hm_sim_desc;
 
 /* statistics of the last hm_sim_batch on this ctx (host side) */

@@ -48,16 +48,22 @@ def _oracle(m, logk, dt, nT, S0, prd):
     return np.array([o[0] for o in outs]), np.array([o[1] for o in outs])
 
 
-@pytest.mark.parametrize("Nx,Ny,N,nT", [(20, 20, 6, 40), (33, 17, 3, 5), (64, 64, 2, 3)])
-def test_forward_ensemble_matches_oracle(Nx, Ny, N, nT):
+# sat_block 0 = automatic: grids of <= 2048 cells run in the fused one-CTA-per-member kernel (hm_small.cu),
+# larger ones on the streamed path; 2 = streamed path with the cluster transport kernel; 1 = streamed path
+# with the streaming transport kernel.
+@pytest.mark.parametrize("Nx,Ny,N,nT,sat_block", [
+    (20, 20, 6, 40, 0), (20, 20, 6, 40, 2), (33, 17, 3, 5, 0), (33, 17, 3, 5, 2), (33, 17, 3, 5, 1),
+    (45, 45, 2, 3, 0), (26, 30, 2, 4, 0), (64, 64, 2, 3, 0)])
+def test_forward_ensemble_matches_oracle(Nx, Ny, N, nT, sat_block):
     from historymatching_b200.sim import run_ensemble
 
     m, grid, logk, cells, rates, prd = _setup(Nx, Ny, N, seed=Nx + Ny)
     dt = 0.025
     S0 = np.zeros(grid.M)
     res = run_ensemble(grid, orr.perm_transf(logk), cells, rates, S0, dt, nT, obs_cell=prd,
-                       history=True, pressure=True, want_substeps=True)
+                       history=True, pressure=True, want_substeps=True, sat_block=sat_block)
     assert not res.status.any()
+    assert (res.stats["kernel_launches"] == 1) == (sat_block == 0 and Nx * Ny <= 2048)  # fused kernel: one launch
     wsats, prods = _oracle(m, logk, dt, nT, S0, prd)
     np.testing.assert_array_equal(res.S_hist[:, 0], 0.0)
     np.testing.assert_allclose(res.S_hist, wsats, rtol=0, atol=SAT_TOL)
@@ -174,7 +180,7 @@ def test_extreme_contrast_floor(golden):
             assert err <= tol, (i, refine, err, tol)
 
 
-@pytest.mark.parametrize("sat_block", [0, 1])
+@pytest.mark.parametrize("sat_block", [0, 1, 2])
 def test_non_default_fluid_and_porosity(sat_block):
     """Viscosity ratio, irreducible saturations and a porosity field (both transport kernels)."""
     from historymatching_b200.sim import GridSpec, run_ensemble
