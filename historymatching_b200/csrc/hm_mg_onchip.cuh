@@ -47,27 +47,42 @@ struct OnchipSmem {
     T *X, *B, *TX, *TY, *DV;
 };
 
+// barrier of the group that runs a level: the whole CTA, or (WARP) the first warp alone for levels of <= 32 cells
+template <bool WARP>
+__device__ __forceinline__ void level_sync() {
+    if (WARP)
+        __syncwarp();
+    else
+        __syncthreads();
+}
+
 __device__ __forceinline__ void cell_ij(int e, int ny, float inv_ny, int& i, int& j) {
     i = __float2int_rd(((float)e + 0.5f) * inv_ny);  // exact for e < 2^22
     j = e - i * ny;
 }
 
+// (A x) at cell e = (i, j) of level l for the all-level vector array xv (level l at xv + mt.off[l])
 template <typename T>
-__device__ __forceinline__ T onchip_Ax(const OnchipMeta& mt, const OnchipSmem<T>& s, int l, int e, int i, int j,
-                                       T pin) {
+__device__ __forceinline__ T onchip_Axv(const OnchipMeta& mt, const OnchipSmem<T>& s, const T* xv, int l, int e, int i,
+                                        int j, T pin) {
     const int ny = mt.ny[l], o = mt.off[l] + e;
-    const T xc = s.X[o];
+    const T xc = xv[o];
     T y = 0;
-    if (i > 0) y = s.TX[o] * (xc - s.X[o - ny]);
-    if (i < mt.nx[l] - 1) y = fma(s.TX[o + ny], xc - s.X[o + ny], y);
-    if (j > 0) y = fma(s.TY[o], xc - s.X[o - 1], y);
-    if (j < ny - 1) y = fma(s.TY[o + 1], xc - s.X[o + 1], y);
+    if (i > 0) y = s.TX[o] * (xc - xv[o - ny]);
+    if (i < mt.nx[l] - 1) y = fma(s.TX[o + ny], xc - xv[o + ny], y);
+    if (j > 0) y = fma(s.TY[o], xc - xv[o - 1], y);
+    if (j < ny - 1) y = fma(s.TY[o + 1], xc - xv[o + 1], y);
     if (e == 0) y = fma(pin, xc, y);
     return y;
 }
+template <typename T>
+__device__ __forceinline__ T onchip_Ax(const OnchipMeta& mt, const OnchipSmem<T>& s, int l, int e, int i, int j,
+                                       T pin) {
+    return onchip_Axv<T>(mt, s, s.X, l, e, i, j, pin);
+}
 
 // nsweep weighted-Jacobi sweeps on level l, in place (new values staged in registers)
-template <typename T, int NT, int PER>
+template <typename T, int NT, int PER, bool WARP = false>
 __device__ __forceinline__ void onchip_smooth(const OnchipMeta& mt, const OnchipSmem<T>& s, int l, T pin,
                                               int nsweep, bool reverse) {
     const int M = mt.M[l], ny = mt.ny[l], o = mt.off[l];
@@ -84,19 +99,19 @@ __device__ __forceinline__ void onchip_smooth(const OnchipMeta& mt, const Onchip
                 xn[k] = s.X[o + e] + wgt * s.DV[o + e] * (s.B[o + e] - onchip_Ax<T>(mt, s, l, e, i, j, pin));
             }
         }
-        __syncthreads();
+        level_sync<WARP>();
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
             const int e = threadIdx.x + k * NT;
             if (e < M) s.X[o + e] = xn[k];
         }
-        __syncthreads();
+        level_sync<WARP>();
     }
 }
 
 // Residual of level l restricted to level l+1 (each coarse thread evaluates its own children);
 // the coarse iterate is reset to zero.
-template <typename T, int NT>
+template <typename T, int NT, bool WARP = false>
 __device__ __forceinline__ void onchip_restrict(const OnchipMeta& mt, const OnchipSmem<T>& s, int l, T pin) {
     const int ny = mt.ny[l], nx = mt.nx[l], o = mt.off[l];
     const int cM = mt.M[l + 1], cny = mt.ny[l + 1], co = mt.off[l + 1];
@@ -118,10 +133,10 @@ __device__ __forceinline__ void onchip_restrict(const OnchipMeta& mt, const Onch
         s.B[co + e] = r;
         s.X[co + e] = 0;
     }
-    __syncthreads();
+    level_sync<WARP>();
 }
 
-template <typename T, int NT>
+template <typename T, int NT, bool WARP = false>
 __device__ __forceinline__ void onchip_prolong(const OnchipMeta& mt, const OnchipSmem<T>& s, int l) {
     const int M = mt.M[l], ny = mt.ny[l], o = mt.off[l], cny = mt.ny[l + 1], co = mt.off[l + 1];
     const float inv = mt.inv_ny[l];
@@ -130,7 +145,7 @@ __device__ __forceinline__ void onchip_prolong(const OnchipMeta& mt, const Onchi
         cell_ij(e, ny, inv, i, j);
         s.X[o + e] += s.X[co + (i >> 1) * cny + (j >> 1)];
     }
-    __syncthreads();
+    level_sync<WARP>();
 }
 
 // Coarse operators of level l+1 from level l (2x2 aggregation, piecewise-constant transfer, Galerkin / 2:
@@ -165,41 +180,40 @@ __device__ __forceinline__ void onchip_coarsen(const OnchipMeta& mt, const Onchi
     __syncthreads();
 }
 
-// One multigrid cycle on the shared-memory hierarchy: X[level 0] = M^-1 B[level 0] (zero initial guess).
-// The cycle (V, or W on the levels of at least `wmin` cells) is an explicit state machine: `left` packs,
-// 4 bits per level, how many cycles are still to be run on that level.
-template <typename T, int NT, int PER>
-__device__ __forceinline__ void onchip_cycle(const OnchipMeta& mt, const OnchipSmem<T>& s, T pinv) {
-    const int M0 = mt.M[0];
-    unsigned long long left = (M0 >= mt.wmin) ? 2ull : 1ull;
-    int l = 0;
+// One multigrid cycle on the shared-memory hierarchy, levels l0 .. mt.n-1: X[l0] = M^-1 B[l0] (X[l0] must be
+// zero on entry).  The cycle (V, or W on the levels of at least `wmin` cells) is an explicit state machine:
+// `left` packs, 4 bits per level, how many cycles are still to be run on that level.
+template <typename T, int NT, int PER, bool WARP = false>
+__device__ __forceinline__ void onchip_cycle(const OnchipMeta& mt, const OnchipSmem<T>& s, T pinv, int l0 = 0) {
+    unsigned long long left = ((mt.M[l0] >= mt.wmin) ? 2ull : 1ull) << (4 * l0);
+    int l = l0;
     bool descend = true;
     while (true) {
         if (descend) {  // start a cycle on level l
             if (l == mt.n - 1) {
                 if (mt.M[l] == 1) {
                     if (threadIdx.x == 0) s.X[mt.off[l]] = s.B[mt.off[l]] * s.DV[mt.off[l]];
-                    __syncthreads();
+                    level_sync<WARP>();
                 } else {
-                    onchip_smooth<T, NT, PER>(mt, s, l, pinv, 3 * kNu, false);
+                    onchip_smooth<T, NT, PER, WARP>(mt, s, l, pinv, 3 * kNu, false);
                 }
                 left -= 1ull << (4 * l);
                 descend = false;
             } else {
-                onchip_smooth<T, NT, PER>(mt, s, l, pinv, kNu, false);
-                onchip_restrict<T, NT>(mt, s, l, pinv);
+                onchip_smooth<T, NT, PER, WARP>(mt, s, l, pinv, kNu, false);
+                onchip_restrict<T, NT, WARP>(mt, s, l, pinv);
                 ++l;
                 left |= ((mt.M[l] >= mt.wmin) ? 2ull : 1ull) << (4 * l);
             }
         } else {  // a cycle on level l has just finished
             if ((left >> (4 * l)) & 15ull) {
                 descend = true;
-            } else if (l == 0) {
+            } else if (l == l0) {
                 break;
             } else {
                 --l;
-                onchip_prolong<T, NT>(mt, s, l);
-                onchip_smooth<T, NT, PER>(mt, s, l, pinv, kNu, true);
+                onchip_prolong<T, NT, WARP>(mt, s, l);
+                onchip_smooth<T, NT, PER, WARP>(mt, s, l, pinv, kNu, true);
                 left -= 1ull << (4 * l);
             }
         }
