@@ -380,7 +380,13 @@ def main():
         pcg_name: (cg_bytes, phase["cg"], stats_acc["cg_kernel_launches"] / 6),
         sat_name: (sat_bytes, phase["saturation"], stats_acc["sat_kernel_launches"]),
     }
-    dom = max(cands, key=lambda k: cands[k][1])
+    # The dominant KERNEL: the transport phase is one kernel, the pressure phase five per iteration (the
+    # largest of them ~30 % of the phase, profiles/launches_*): transport dominates unless it is < 0.35 x CG.
+    fused = stats_acc["sat_kernel_launches"] == 0  # small grids: the whole simulator is one kernel (hm_small.cu)
+    dom = sat_name if (phase["saturation"] > 0.35 * phase["cg"] and not fused) else pcg_name
+    if fused:
+        dom = pcg_name = "k_sim_small (whole forward run of a member in one CTA, shared-memory resident; latency bound)"
+        cands[dom] = (cg_bytes + sat_bytes, phase["cg"], args.steps)
     b, t_ms, n_launch = cands[dom]
     achieved = b / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
     roofline = dict(bound="hbm", kernel=dom, achieved=achieved, peak=hbm, unit="GB/s", frac=achieved / hbm,
@@ -390,14 +396,20 @@ def main():
     if dom == sat_name and cluster:
         # the cluster kernel touches HBM once per time step (40 B/cell: S in, 3 flux reads incl. pads, S out),
         # the streaming model above counts 32 B per sub-step: frac > 1 is on-chip reuse, the binding
-        # resource is the FP64 pipe (~22 FP64 instructions per cell and sub-step, 64 lanes/clk/SM)
+        # resource is the FP64 pipe (13 FP64 instructions per cell and sub-step, 64 lanes/clk/SM)
         nts_mean = sat_member_substeps / max(1, N_loc * wl["nTime"] * args.steps)
         sm_hz = (sampler.summary()["sm_mhz"] or 1965.0) * 1e6
         roofline["on_chip_reuse_factor"] = 32.0 * nts_mean / 40.0
         roofline["hbm_bytes_per_launch_actual"] = 40.0 * M * N_loc
-        roofline["fp64_pipe_frac"] = 22.0 * M * sat_member_substeps / (t_ms * 1e-3) / (148 * 64 * sm_hz)
-        roofline["note"] = ("streaming model of SURVEY 8(d); kernel is FP64-pipe bound, not HBM bound: "
-                            "frac > 1 is the on-chip reuse of the register/DSMEM-resident sub-step loop")
+        roofline["fp64_pipe_frac"] = 13.0 * M * sat_member_substeps / (t_ms * 1e-3) / (148 * 64 * sm_hz)
+        roofline["note"] = ("streaming model of SURVEY 8(d); the kernel keeps S and the upwind coefficients in "
+                            "registers for all sub-steps of a time step, so it is FP64-pipe / latency bound, not "
+                            "HBM bound: frac > 1 is the on-chip reuse factor at work")
+        prof = os.path.join(ROOT, "profiles", "ncu_k_sat_cluster.json")
+        if os.path.exists(prof) and (wl["Nx"], wl["Ny"], N_loc) == (128, 128, 1024):
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at exactly this configuration
+            # (ncu --set full capture, profiles/ncu_k_sat_cluster.txt)
+            roofline["traffic"] = json.load(open(prof))[0]["traffic_MB"] * 1e6
     other = sat_name if dom != sat_name else pcg_name
     ob, ot, _ = cands[other]
 

@@ -47,15 +47,6 @@ struct OnchipSmem {
     T *X, *B, *TX, *TY, *DV;
 };
 
-// barrier of the group that runs a level: the whole CTA, or (WARP) the first warp alone for levels of <= 32 cells
-template <bool WARP>
-__device__ __forceinline__ void level_sync() {
-    if (WARP)
-        __syncwarp();
-    else
-        __syncthreads();
-}
-
 __device__ __forceinline__ void cell_ij(int e, int ny, float inv_ny, int& i, int& j) {
     i = __float2int_rd(((float)e + 0.5f) * inv_ny);  // exact for e < 2^22
     j = e - i * ny;
@@ -81,13 +72,25 @@ __device__ __forceinline__ T onchip_Ax(const OnchipMeta& mt, const OnchipSmem<T>
     return onchip_Axv<T>(mt, s, s.X, l, e, i, j, pin);
 }
 
-// nsweep weighted-Jacobi sweeps on level l, in place (new values staged in registers)
-template <typename T, int NT, int PER, bool WARP = false>
+// nsweep weighted-Jacobi sweeps on level l, in place (new values staged in registers).  zero_guess: the
+// iterate is known to be zero, so the first sweep is x = w0 D^-1 b without a stencil (and one barrier).
+template <typename T, int NT, int PER>
 __device__ __forceinline__ void onchip_smooth(const OnchipMeta& mt, const OnchipSmem<T>& s, int l, T pin,
-                                              int nsweep, bool reverse) {
+                                              int nsweep, bool reverse, bool zero_guess = false) {
     const int M = mt.M[l], ny = mt.ny[l], o = mt.off[l];
     const float inv = mt.inv_ny[l];
-    for (int sw = 0; sw < nsweep; ++sw) {
+    int sw = 0;
+    if (zero_guess) {
+        const T wgt = (T)cheb_w(reverse ? kNu - 1 : 0);
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int e = threadIdx.x + k * NT;
+            if (e < M) s.X[o + e] = (T)0 + wgt * s.DV[o + e] * (s.B[o + e] - (T)0);
+        }
+        __syncthreads();
+        sw = 1;
+    }
+    for (; sw < nsweep; ++sw) {
         const T wgt = (T)cheb_w(reverse ? (kNu - 1 - sw % kNu) : sw % kNu);
         T xn[PER];
 #pragma unroll
@@ -99,19 +102,19 @@ __device__ __forceinline__ void onchip_smooth(const OnchipMeta& mt, const Onchip
                 xn[k] = s.X[o + e] + wgt * s.DV[o + e] * (s.B[o + e] - onchip_Ax<T>(mt, s, l, e, i, j, pin));
             }
         }
-        level_sync<WARP>();
+        __syncthreads();
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
             const int e = threadIdx.x + k * NT;
             if (e < M) s.X[o + e] = xn[k];
         }
-        level_sync<WARP>();
+        __syncthreads();
     }
 }
 
 // Residual of level l restricted to level l+1 (each coarse thread evaluates its own children);
 // the coarse iterate is reset to zero.
-template <typename T, int NT, bool WARP = false>
+template <typename T, int NT>
 __device__ __forceinline__ void onchip_restrict(const OnchipMeta& mt, const OnchipSmem<T>& s, int l, T pin) {
     const int ny = mt.ny[l], nx = mt.nx[l], o = mt.off[l];
     const int cM = mt.M[l + 1], cny = mt.ny[l + 1], co = mt.off[l + 1];
@@ -133,10 +136,10 @@ __device__ __forceinline__ void onchip_restrict(const OnchipMeta& mt, const Onch
         s.B[co + e] = r;
         s.X[co + e] = 0;
     }
-    level_sync<WARP>();
+    __syncthreads();
 }
 
-template <typename T, int NT, bool WARP = false>
+template <typename T, int NT>
 __device__ __forceinline__ void onchip_prolong(const OnchipMeta& mt, const OnchipSmem<T>& s, int l) {
     const int M = mt.M[l], ny = mt.ny[l], o = mt.off[l], cny = mt.ny[l + 1], co = mt.off[l + 1];
     const float inv = mt.inv_ny[l];
@@ -145,7 +148,7 @@ __device__ __forceinline__ void onchip_prolong(const OnchipMeta& mt, const Onchi
         cell_ij(e, ny, inv, i, j);
         s.X[o + e] += s.X[co + (i >> 1) * cny + (j >> 1)];
     }
-    level_sync<WARP>();
+    __syncthreads();
 }
 
 // Coarse operators of level l+1 from level l (2x2 aggregation, piecewise-constant transfer, Galerkin / 2:
@@ -180,40 +183,90 @@ __device__ __forceinline__ void onchip_coarsen(const OnchipMeta& mt, const Onchi
     __syncthreads();
 }
 
+// Dense inverse of the operator of level l (n = mt.M[l] <= 32 cells; SPD thanks to the pin) -> A[n][n]
+// (row pitch n), by Gauss-Jordan elimination without pivoting in ONE warp: lane r owns row r.  Always FP64,
+// also under an FP32 hierarchy: the pinned operator is nearly singular (the constant mode is held by the pin
+// alone) and its inverse has to be accurate for the cycle to stay symmetric positive definite.
+constexpr int kDenseMax = 32;
+template <typename T>
+__device__ __forceinline__ void warp_dense_inverse(int n, int nx, int ny, const T* __restrict__ TX,
+                                                   const T* __restrict__ TY, double pin, double* A /* [n][n] */) {
+    const int r = threadIdx.x & 31;
+    if (r < n) {
+        const int i = r / ny, j = r - i * ny;
+        const double txl = i > 0 ? (double)TX[r] : 0.0, txh = i < nx - 1 ? (double)TX[r + ny] : 0.0;
+        const double tyl = j > 0 ? (double)TY[r] : 0.0, tyh = j < ny - 1 ? (double)TY[r + 1] : 0.0;
+        for (int c = 0; c < n; ++c) A[r * n + c] = 0.0;
+        A[r * n + r] = tyl + tyh + txl + txh + (r == 0 ? pin : 0.0);
+        if (i > 0) A[r * n + r - ny] = -txl;
+        if (i < nx - 1) A[r * n + r + ny] = -txh;
+        if (j > 0) A[r * n + r - 1] = -tyl;
+        if (j < ny - 1) A[r * n + r + 1] = -tyh;
+    }
+    __syncwarp();
+    for (int k = 0; k < n; ++k) {
+        const double pk = 1.0 / A[k * n + k];
+        __syncwarp();
+        if (r < n && r != k) {
+            const double f = A[r * n + k] * pk;
+            for (int c = 0; c < n; ++c)
+                if (c != k) A[r * n + c] = fma(-f, A[k * n + c], A[r * n + c]);
+            A[r * n + k] = -f;
+        }
+        __syncwarp();
+        if (r < n && r != k) A[k * n + r] *= pk;
+        if (r == k) A[k * n + k] = pk;
+        __syncwarp();
+    }
+}
+
 // One multigrid cycle on the shared-memory hierarchy, levels l0 .. mt.n-1: X[l0] = M^-1 B[l0] (X[l0] must be
 // zero on entry).  The cycle (V, or W on the levels of at least `wmin` cells) is an explicit state machine:
-// `left` packs, 4 bits per level, how many cycles are still to be run on that level.
-template <typename T, int NT, int PER, bool WARP = false>
-__device__ __forceinline__ void onchip_cycle(const OnchipMeta& mt, const OnchipSmem<T>& s, T pinv, int l0 = 0) {
+// `left` packs, 4 bits per level, how many cycles are still to be run on that level.  The coarsest level
+// mt.n-1 is solved exactly with its dense inverse `Ainv` (row pitch mt.M[mt.n-1]) when that is given, else
+// by 3 kNu sweeps (a single cell: division).
+template <typename T, int NT, int PER>
+__device__ __forceinline__ void onchip_cycle(const OnchipMeta& mt, const OnchipSmem<T>& s, T pinv, int l0 = 0,
+                                             const double* Ainv = nullptr) {
     unsigned long long left = ((mt.M[l0] >= mt.wmin) ? 2ull : 1ull) << (4 * l0);
     int l = l0;
-    bool descend = true;
+    bool descend = true, fresh = true;  // fresh: the iterate of level l is still zero
     while (true) {
         if (descend) {  // start a cycle on level l
             if (l == mt.n - 1) {
-                if (mt.M[l] == 1) {
-                    if (threadIdx.x == 0) s.X[mt.off[l]] = s.B[mt.off[l]] * s.DV[mt.off[l]];
-                    level_sync<WARP>();
+                const int n = mt.M[l], o = mt.off[l];
+                if (Ainv) {
+                    if ((int)threadIdx.x < n) {
+                        double acc = 0.0;  // exact solve (also on a W-cycle revisit, where it changes nothing)
+                        for (int c = 0; c < n; ++c) acc = fma(Ainv[threadIdx.x * n + c], (double)s.B[o + c], acc);
+                        s.X[o + threadIdx.x] = (T)acc;
+                    }
+                    __syncthreads();
+                } else if (n == 1) {
+                    if (threadIdx.x == 0) s.X[o] = s.B[o] * s.DV[o];
+                    __syncthreads();
                 } else {
-                    onchip_smooth<T, NT, PER, WARP>(mt, s, l, pinv, 3 * kNu, false);
+                    onchip_smooth<T, NT, PER>(mt, s, l, pinv, 3 * kNu, false, fresh);
                 }
                 left -= 1ull << (4 * l);
                 descend = false;
             } else {
-                onchip_smooth<T, NT, PER, WARP>(mt, s, l, pinv, kNu, false);
-                onchip_restrict<T, NT, WARP>(mt, s, l, pinv);
+                onchip_smooth<T, NT, PER>(mt, s, l, pinv, kNu, false, fresh);
+                onchip_restrict<T, NT>(mt, s, l, pinv);
                 ++l;
+                fresh = true;
                 left |= ((mt.M[l] >= mt.wmin) ? 2ull : 1ull) << (4 * l);
             }
         } else {  // a cycle on level l has just finished
+            fresh = false;
             if ((left >> (4 * l)) & 15ull) {
                 descend = true;
             } else if (l == l0) {
                 break;
             } else {
                 --l;
-                onchip_prolong<T, NT, WARP>(mt, s, l);
-                onchip_smooth<T, NT, PER, WARP>(mt, s, l, pinv, kNu, true);
+                onchip_prolong<T, NT>(mt, s, l);
+                onchip_smooth<T, NT, PER>(mt, s, l, pinv, kNu, true);
                 left -= 1ull << (4 * l);
             }
         }

@@ -71,6 +71,49 @@ __device__ __forceinline__ T stencil(const T* xr, int col, int ny, const T* __re
     return y;
 }
 
+// One stencil evaluation per cell of a whole grid row by a warp, handing (col, c, x_c, 1/diag, b, (A x)_c) to
+// `emit`.  NC != 0 (row length 32 NC known at compile time): the operator values of all the lane's cells are
+// loaded first - 6 NC independent global loads in flight per lane - and consumed afterwards; with a runtime
+// row length the loads of one cell are only issued after the previous cell's result is stored, and the
+// kernels stall on L2 latency (the shared-memory footprint leaves almost no L1).  Same arithmetic as stencil().
+template <typename T, typename TB, int NC, bool STAGE, typename F>
+__device__ __forceinline__ void row_stencil(const T* xr, int ny, int lane, int c0, int li0,
+                                            const T* __restrict__ TX, const T* __restrict__ TY,
+                                            const T* __restrict__ dinv, const TB* __restrict__ b, const T* ds,
+                                            const T* bs, T pinv, F&& emit) {
+    if constexpr (NC != 0) {
+        T tx0[NC], tx1[NC], ty0[NC], ty1[NC], dv[NC], bv[NC];
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
+            const int col = lane + 32 * q, c = c0 + col;
+            tx0[q] = TX[c];
+            tx1[q] = TX[c + ny];
+            ty0[q] = TY[c];
+            ty1[q] = TY[c + 1];
+            dv[q] = STAGE ? ds[li0 + col] : dinv[c];
+            bv[q] = STAGE ? bs[li0 + col] : (T)b[c];
+        }
+        asm volatile("" ::: "memory");  // keep every global load above the shared-memory phase
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
+            const int col = lane + 32 * q, c = c0 + col;
+            const T xc = xr[col];
+            T y = tx0[q] * (xc - xr[col - ny]);
+            y = fma(tx1[q], xc - xr[col + ny], y);
+            y = fma(ty0[q], xc - xr[col - 1], y);
+            y = fma(ty1[q], xc - xr[col + 1], y);
+            if (c == 0) y = fma(pinv, xc, y);
+            emit(col, c, xc, dv[q], bv[q], y);
+        }
+    } else {
+        for (int col = lane; col < ny; col += 32) {
+            const int c = c0 + col;
+            const T dvv = STAGE ? ds[li0 + col] : dinv[c], bvv = STAGE ? bs[li0 + col] : (T)b[c];
+            emit(col, c, xr[col], dvv, bvv, stencil<T>(xr, col, ny, TX + c, TY + c, c == 0, pinv));
+        }
+    }
+}
+
 // ---- hierarchy ------------------------------------------------------------------------------
 // FP64 level-0 operator -> arithmetic type of the preconditioner
 template <typename T>
@@ -118,7 +161,7 @@ __global__ void k_mg_coarsen(int nm, Lvl<T> f, int cnx, int cny, T* __restrict__
 // sweeps rows [r0-1, r1+1) are exact; then the residual on the tile rows and its 2x2 sums (the
 // coarse right-hand side).  b, the operator and the sweeps ping-pong in shared memory; a warp
 // walks whole grid rows (lanes along the contiguous index): no integer division.
-template <typename T, bool TOP>
+template <typename T, bool TOP, int NY = 0>
 __global__ void __launch_bounds__(kThreads)
 k_mg_down(Lvl<T> f, int cny, T* __restrict__ cb, const double* __restrict__ pin, const int* __restrict__ done) {
     using TB = typename std::conditional<TOP, double, T>::type;
@@ -126,7 +169,8 @@ k_mg_down(Lvl<T> f, int cny, T* __restrict__ cb, const double* __restrict__ pin,
     const int m = blockIdx.x / f.nTiles, t = blockIdx.x % f.nTiles;
     if (done[m]) return;
     constexpr int H = kNu;  // halo rows of the first sweep
-    const int ny = f.ny, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nW = kThreads >> 5;
+    // NY != 0: row length known at compile time, the column loops unroll fully (independent loads in flight)
+    const int ny = NY ? NY : f.ny, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nW = kThreads >> 5;
     const int r0 = t * f.R, r1 = min(r0 + f.R, f.nx), rows = r1 - r0;
     const int64_t off = (int64_t)m * f.M;
     const TB* __restrict__ b = static_cast<const TB*>(f.b) + off;
@@ -146,6 +190,7 @@ k_mg_down(Lvl<T> f, int cny, T* __restrict__ cb, const double* __restrict__ pin,
         const int row = r0 - H + lr;
         const bool in = row >= 0 && row < f.nx;
         const int c0 = row * ny;
+#pragma unroll
         for (int col = lane; col < ny; col += 32) {
             const T bv = in ? (T)b[c0 + col] : (T)0, dv = in ? dinv[c0 + col] : (T)0;
             if (STAGE) {
@@ -165,11 +210,9 @@ k_mg_down(Lvl<T> f, int cny, T* __restrict__ cb, const double* __restrict__ pin,
             if (row < 0 || row >= f.nx) continue;
             const int c0 = row * ny;
             const T* xr = xa + lr * ny;
-            for (int col = lane; col < ny; col += 32) {
-                const int c = c0 + col, li = lr * ny + col;
-                const T dv = STAGE ? ds[li] : dinv[c], bv = STAGE ? bs[li] : (T)b[c];
-                xb[li] = xr[col] + w * dv * (bv - stencil<T>(xr, col, ny, TX + c, TY + c, c == 0, pinv));
-            }
+            T* xo = xb + lr * ny;
+            row_stencil<T, TB, NY / 32, STAGE>(xr, ny, lane, c0, lr * ny, TX, TY, dinv, b, ds, bs, pinv,
+                                               [&](int col, int, T xc, T dv, T bv, T y) { xo[col] = xc + w * dv * (bv - y); });
         }
         __syncthreads();
         T* tsw = xa;
@@ -180,12 +223,13 @@ k_mg_down(Lvl<T> f, int cny, T* __restrict__ cb, const double* __restrict__ pin,
     for (int lr = warp; lr < rows; lr += nW) {
         const int c0 = (r0 + lr) * ny;
         const T* xr = xa + (lr + H) * ny;
-        for (int col = lane; col < ny; col += 32) {
-            const int c = c0 + col;
-            f.xa[off + c] = xr[col];
-            const T bv = STAGE ? bs[(lr + H) * ny + col] : (T)b[c];
-            xb[lr * ny + col] = bv - stencil<T>(xr, col, ny, TX + c, TY + c, c == 0, pinv);
-        }
+        T* xo = xb + lr * ny;
+        T* xg = f.xa + off;
+        row_stencil<T, TB, NY / 32, STAGE>(xr, ny, lane, c0, (lr + H) * ny, TX, TY, dinv, b, ds, bs, pinv,
+                                           [&](int col, int c, T xc, T, T bv, T y) {
+                                               xg[c] = xc;
+                                               xo[col] = bv - y;
+                                           });
     }
     __syncthreads();
     const T* res = xb;
@@ -211,7 +255,7 @@ k_mg_down(Lvl<T> f, int cny, T* __restrict__ cb, const double* __restrict__ pin,
 // ---- streamed level: prolongation + post-smoothing (+ (r,z) on the top level) ----------------------
 // x = xa + P xc on rows [r0-NU, r1+NU), then NU sweeps (weights in reverse order) on shrinking row
 // ranges; the last sweep covers exactly the tile rows and is written to xb.
-template <typename T, bool TOP>
+template <typename T, bool TOP, int NY = 0>
 __global__ void __launch_bounds__(kThreads)
 k_mg_up(Lvl<T> f, int cny, const T* __restrict__ cx, const double* __restrict__ pin,
         const int* __restrict__ done, double* __restrict__ part_rz) {
@@ -221,7 +265,8 @@ k_mg_up(Lvl<T> f, int cny, const T* __restrict__ cx, const double* __restrict__ 
     const int m = blockIdx.x / f.nTiles, t = blockIdx.x % f.nTiles;
     if (done[m]) return;
     constexpr int H = kNu;
-    const int ny = f.ny, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nW = kThreads >> 5;
+    // NY != 0: row length known at compile time, the column loops unroll fully (independent loads in flight)
+    const int ny = NY ? NY : f.ny, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nW = kThreads >> 5;
     const int r0 = t * f.R, r1 = min(r0 + f.R, f.nx), rows = r1 - r0;
     const int64_t off = (int64_t)m * f.M;
     const int cM = ((f.nx + 1) / 2) * cny;
@@ -244,6 +289,7 @@ k_mg_up(Lvl<T> f, int cny, const T* __restrict__ cx, const double* __restrict__ 
         const bool in = row >= 0 && row < f.nx;
         const int c0 = row * ny;
         const T* xcr = xc + (row >> 1) * cny;
+#pragma unroll
         for (int col = lane; col < ny; col += 32) {
             if (STAGE) {
                 bs[lr * ny + col] = in ? (T)b[c0 + col] : (T)0;
@@ -262,11 +308,9 @@ k_mg_up(Lvl<T> f, int cny, const T* __restrict__ cx, const double* __restrict__ 
             if (row < 0 || row >= f.nx) continue;
             const int c0 = row * ny;
             const T* xr = xa + lr * ny;
-            for (int col = lane; col < ny; col += 32) {
-                const int c = c0 + col, li = lr * ny + col;
-                const T dv = STAGE ? ds[li] : dinv[c], bv = STAGE ? bs[li] : (T)b[c];
-                xb[li] = xr[col] + w * dv * (bv - stencil<T>(xr, col, ny, TX + c, TY + c, c == 0, pinv));
-            }
+            T* xo = xb + lr * ny;
+            row_stencil<T, TB, NY / 32, STAGE>(xr, ny, lane, c0, lr * ny, TX, TY, dinv, b, ds, bs, pinv,
+                                               [&](int col, int, T xc, T dv, T bv, T y) { xo[col] = xc + w * dv * (bv - y); });
         }
         __syncthreads();
         T* tsw = xa;
@@ -277,13 +321,12 @@ k_mg_up(Lvl<T> f, int cny, const T* __restrict__ cx, const double* __restrict__ 
     for (int lr = warp; lr < rows; lr += nW) {
         const int c0 = (r0 + lr) * ny;
         const T* xr = xa + (lr + H) * ny;
-        for (int col = lane; col < ny; col += 32) {
-            const int c = c0 + col, li = (lr + H) * ny + col;
-            const T dv = STAGE ? ds[li] : dinv[c], bv = STAGE ? bs[li] : (T)b[c];
-            const T v = xr[col] + (T)cheb_w(0) * dv * (bv - stencil<T>(xr, col, ny, TX + c, TY + c, c == 0, pinv));
-            xout[c] = (TB)v;
-            if (TOP) dot = fma((double)b[c], (double)v, dot);
-        }
+        row_stencil<T, TB, NY / 32, STAGE>(xr, ny, lane, c0, (lr + H) * ny, TX, TY, dinv, b, ds, bs, pinv,
+                                           [&](int, int c, T xc, T dv, T bv, T y) {
+                                               const T v = xc + (T)cheb_w(0) * dv * (bv - y);
+                                               xout[c] = (TB)v;
+                                               if (TOP) dot = fma((double)bv, (double)v, dot);
+                                           });
     }
     if (TOP) {
         dot = block_sum(dot, red);
@@ -292,15 +335,35 @@ k_mg_up(Lvl<T> f, int cny, const T* __restrict__ cx, const double* __restrict__ 
 }
 
 // ---- all small levels in shared memory (device functions: hm_mg_onchip.cuh) -------------------------
+// Dense inverse of the coarsest on-chip level (<= 32 cells) of every member, once per solve: one warp per
+// member, Gauss-Jordan in shared memory (warp_dense_inverse), result [member][n][n] in global memory.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_mg_dense_inverse(int nm, int n, int nx, int ny, const T* __restrict__ TX, const T* __restrict__ TY,
+                   const double* __restrict__ pin, double* __restrict__ Ainv) {
+    double* sm = smem_as<double>();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = blockIdx.x * 8 + warp;
+    if (m >= nm) return;
+    double* A = sm + warp * n * n;
+    warp_dense_inverse<T>(n, nx, ny, TX + (int64_t)m * n, TY + (int64_t)m * n, pin[m], A);
+    for (int e = lane; e < n * n; e += 32) Ainv[(int64_t)m * n * n + e] = A[e];
+}
+
 // One CTA per member runs the cycle (V, or W on the levels of at least `wmin` cells) on the shared-memory
-// hierarchy.
+// hierarchy; the coarsest level (<= 32 cells) is solved exactly with the precomputed dense inverse.
 template <typename T>
 __global__ void __launch_bounds__(kOnchipThreads, 1)
 k_mg_onchip(const __grid_constant__ OnchipMeta mt, const T* __restrict__ b_in, T* __restrict__ x_out,
-            const double* __restrict__ pin, const int* __restrict__ done) {
+            const double* __restrict__ pin, const int* __restrict__ done, const double* __restrict__ Ainv_g) {
     T* sm = smem_as<T>();
+    __shared__ double Ainv[kDenseMax * kDenseMax];
     const int m = blockIdx.x;
     if (done[m]) return;
+    {
+        const int nn = mt.M[mt.n - 1] * mt.M[mt.n - 1];
+        for (int e = threadIdx.x; e < nn; e += kOnchipThreads) Ainv[e] = Ainv_g[(int64_t)m * nn + e];
+    }
     OnchipSmem<T> s;
     s.X = sm;
     s.B = sm + mt.total;
@@ -325,7 +388,7 @@ k_mg_onchip(const __grid_constant__ OnchipMeta mt, const T* __restrict__ b_in, T
     }
     __syncthreads();
     const T pinv = (T)pin[m];
-    onchip_cycle<T, kOnchipThreads, kOnchipCells / kOnchipThreads>(mt, s, pinv);
+    onchip_cycle<T, kOnchipThreads, kOnchipCells / kOnchipThreads>(mt, s, pinv, 0, Ainv);
     for (int e = threadIdx.x; e < M0; e += kOnchipThreads) x_out[(int64_t)m * M0 + e] = s.X[e];
 }
 
@@ -424,6 +487,7 @@ __global__ void k_cg_check(int nm, int nTiles, int k, double tol2, const double*
 
 // p' = z + beta p ; Ap' ; partial (p',Ap').  Parity buffers: iteration k reads (r,z)[k&1] and
 // p[k&1], writes p[(k+1)&1].
+template <int NY = 0>
 __global__ void __launch_bounds__(kThreads)
 k_cg_spmv(Geo g, int k, const double* __restrict__ Z, const double* __restrict__ Pin,
           double* __restrict__ Pout, double* __restrict__ AP, const double* __restrict__ TXl,
@@ -442,11 +506,12 @@ k_cg_spmv(Geo g, int k, const double* __restrict__ Z, const double* __restrict__
     }
     const int r0 = t * g.R, r1 = min(r0 + g.R, g.Nx), rows = r1 - r0;
     const int64_t off = (int64_t)m * g.M;
-    const int ny = g.Ny, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nW = kThreads >> 5;
+    const int ny = NY ? NY : g.Ny, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nW = kThreads >> 5;
     for (int lr = warp; lr < rows + 2; lr += nW) {
         const int row = r0 - 1 + lr;
         const bool in = row >= 0 && row < g.Nx, own = row >= r0 && row < r1;
         const int64_t c0 = off + (int64_t)row * ny;
+#pragma unroll
         for (int col = lane; col < ny; col += 32) {
             double pn = 0.0;
             if (in) {
@@ -462,6 +527,7 @@ k_cg_spmv(Geo g, int k, const double* __restrict__ Z, const double* __restrict__
     for (int lr = warp; lr < rows; lr += nW) {
         const int c0 = (r0 + lr) * ny;
         const double* xr = sm + (lr + 1) * ny;
+#pragma unroll
         for (int col = lane; col < ny; col += 32) {
             const int c = c0 + col;
             const double ap = stencil(xr, col, ny, TXl + off + c, TYl + off + c, c == 0, pinv);
@@ -522,6 +588,7 @@ struct MgHierarchy {
     int* done = nullptr;
     double* part_rz = nullptr;
     size_t nPart = 0;
+    double* Ainv = nullptr;  // [member][n][n]: dense inverse (FP64) of the coarsest level
 
     size_t smem_level(int l) const { return (size_t)(sizeof(T) == 4 ? 4 : 2) * (lv[l].R + 2 * kNu) * lv[l].ny * sizeof(T); }
 
@@ -549,10 +616,12 @@ struct MgHierarchy {
             }
             L.nTiles = (nx + L.R - 1) / L.R;
             ++nLev;
-            if ((nx == 1 && ny == 1) || nLev == kMaxLevels) break;
+            // the hierarchy ends at the first level (below level 0) of <= 32 cells: it is solved exactly
+            if ((nLev > 1 && nx * ny <= kDenseMax) || (nx == 1 && ny == 1) || nLev == kMaxLevels) break;
             nx = (nx + 1) / 2;
             ny = (ny + 1) / 2;
         }
+        HM_REQUIRE(lv[nLev - 1].M <= kDenseMax, "multigrid hierarchy too deep");
         firstOn = 1;
         while (firstOn < nLev && lv[firstOn].M > kOnchipCells) ++firstOn;
         HM_REQUIRE(firstOn < nLev, "grid too large for the multigrid hierarchy");
@@ -618,6 +687,15 @@ struct MgHierarchy {
         mt.wmin = wcycle ? kWcycleMinCells : 0x7fffffff;
         smemOn = (size_t)5 * o * sizeof(T);
         HM_CUDA(cudaFuncSetAttribute(k_mg_onchip<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemOn));
+        {   // dense inverse of the coarsest level, one warp per member
+            const Lvl<T>& L = lv[nLev - 1];
+            snprintf(name, sizeof name, "mg%s.Ainv", tag);
+            HM_CHECK(ctx->ws.get(name, (size_t)nm * L.M * L.M, &Ainv));
+            const size_t smd = (size_t)8 * L.M * L.M * sizeof(double);
+            HM_CUDA(cudaFuncSetAttribute(k_mg_dense_inverse<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smd));
+            k_mg_dense_inverse<T><<<(nm + 7) / 8, 256, smd, st>>>(nm, L.M, L.nx, L.ny, L.TX, L.TY, pin, Ainv);
+            ctx->sim_stats.kernel_launches += 1;
+        }
         size_t smax = 0;
         for (int l = 0; l < firstOn; ++l) smax = std::max(smax, smem_level(l));
         HM_REQUIRE(smax <= 200 * 1024, "row tile of a streamed multigrid level exceeds shared memory");
@@ -626,6 +704,10 @@ struct MgHierarchy {
             HM_CUDA(cudaFuncSetAttribute(k_mg_down<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
             HM_CUDA(cudaFuncSetAttribute(k_mg_up<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
             HM_CUDA(cudaFuncSetAttribute(k_mg_up<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+            HM_CUDA(cudaFuncSetAttribute(k_mg_down<T, true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+            HM_CUDA(cudaFuncSetAttribute(k_mg_up<T, true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+            HM_CUDA(cudaFuncSetAttribute(k_mg_down<T, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+            HM_CUDA(cudaFuncSetAttribute(k_mg_up<T, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
         }
         return HM_OK;
     }
@@ -635,21 +717,32 @@ struct MgHierarchy {
         cudaStream_t st = ctx->stream;
         for (int l = 0; l < firstOn; ++l) {
             T* cb = static_cast<T*>(lv[l + 1].b);
-            if (l == 0)
-                k_mg_down<T, true><<<nm * lv[l].nTiles, kThreads, smem_level(l), st>>>(lv[l], lv[l + 1].ny, cb, pin, done);
+            const int grid = nm * lv[l].nTiles;
+            const size_t sm = smem_level(l);
+            if (l == 0 && lv[0].ny == 128)
+                k_mg_down<T, true, 128><<<grid, kThreads, sm, st>>>(lv[l], lv[l + 1].ny, cb, pin, done);
+            else if (l == 0 && lv[0].ny == 512)
+                k_mg_down<T, true, 512><<<grid, kThreads, sm, st>>>(lv[l], lv[l + 1].ny, cb, pin, done);
+            else if (l == 0)
+                k_mg_down<T, true><<<grid, kThreads, sm, st>>>(lv[l], lv[l + 1].ny, cb, pin, done);
             else
-                k_mg_down<T, false><<<nm * lv[l].nTiles, kThreads, smem_level(l), st>>>(lv[l], lv[l + 1].ny, cb, pin, done);
+                k_mg_down<T, false><<<grid, kThreads, sm, st>>>(lv[l], lv[l + 1].ny, cb, pin, done);
         }
         k_mg_onchip<T><<<nm, kOnchipThreads, smemOn, st>>>(mt, static_cast<const T*>(lv[firstOn].b),
-                                                            static_cast<T*>(lv[firstOn].xb), pin, done);
+                                                            static_cast<T*>(lv[firstOn].xb), pin, done, Ainv);
         for (int l = firstOn - 1; l >= 0; --l) {
             const T* cx = static_cast<const T*>(lv[l + 1].xb);
-            if (l == 0)
-                k_mg_up<T, true><<<nm * lv[l].nTiles, kThreads, smem_level(l), st>>>(lv[l], lv[l + 1].ny, cx, pin, done,
-                                                                                      part_rz + parity * nPart);
+            const int grid = nm * lv[l].nTiles;
+            const size_t sm = smem_level(l);
+            double* prz = part_rz + parity * nPart;
+            if (l == 0 && lv[0].ny == 128)
+                k_mg_up<T, true, 128><<<grid, kThreads, sm, st>>>(lv[l], lv[l + 1].ny, cx, pin, done, prz);
+            else if (l == 0 && lv[0].ny == 512)
+                k_mg_up<T, true, 512><<<grid, kThreads, sm, st>>>(lv[l], lv[l + 1].ny, cx, pin, done, prz);
+            else if (l == 0)
+                k_mg_up<T, true><<<grid, kThreads, sm, st>>>(lv[l], lv[l + 1].ny, cx, pin, done, prz);
             else
-                k_mg_up<T, false><<<nm * lv[l].nTiles, kThreads, smem_level(l), st>>>(lv[l], lv[l + 1].ny, cx, pin, done,
-                                                                                       nullptr);
+                k_mg_up<T, false><<<grid, kThreads, sm, st>>>(lv[l], lv[l + 1].ny, cx, pin, done, nullptr);
         }
         ctx->sim_stats.kernel_launches += 2 * firstOn + 1;
         ctx->sim_stats.cg_kernel_launches += 2 * firstOn + 1;
@@ -686,7 +779,9 @@ int pressure_solve(hm_ctx* ctx, const Geo& g, const Wells& w, int step, int nm, 
     if (smem1 > 48 * 1024) {
         HM_CUDA(cudaFuncSetAttribute(k_cg_init<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
         HM_CUDA(cudaFuncSetAttribute(k_cg_init<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-        HM_CUDA(cudaFuncSetAttribute(k_cg_spmv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        HM_CUDA(cudaFuncSetAttribute(k_cg_spmv<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        HM_CUDA(cudaFuncSetAttribute(k_cg_spmv<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        HM_CUDA(cudaFuncSetAttribute(k_cg_spmv<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     }
 
     // ---- multigrid hierarchy: FP64 V-cycle (precond 0), FP64 W-cycle (2) or FP32 V-cycle (3) ------------
@@ -728,8 +823,9 @@ int pressure_solve(hm_ctx* ctx, const Geo& g, const Wells& w, int step, int nm, 
             double* Pout = cur ? Pa : Pb;
             k_cg_check<<<chk_blocks, 128, 0, st>>>(nm, g.nTiles, k, tol2, part_rr, bb, done, iters, counters);
             if (!jacobi) precondition(cur);
-            k_cg_spmv<<<grid, kThreads, smem1, st>>>(g, k, Z, Pin, Pout, AP, TXl, TYl, pin, part_rz + cur * nPart,
-                                                      part_rz + nxt * nPart, part_pAp, done);
+            auto spmv = g.Ny == 128 ? k_cg_spmv<128> : g.Ny == 512 ? k_cg_spmv<512> : k_cg_spmv<0>;
+            spmv<<<grid, kThreads, smem1, st>>>(g, k, Z, Pin, Pout, AP, TXl, TYl, pin, part_rz + cur * nPart,
+                                                part_rz + nxt * nPart, part_pAp, done);
             if (jacobi)
                 k_cg_update<true><<<grid, kThreads, 0, st>>>(g, P, Rv, Z, Pout, AP, dinv, part_rz + cur * nPart,
                                                               part_pAp, part_rz + nxt * nPart, part_rr, done);
