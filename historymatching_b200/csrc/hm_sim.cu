@@ -552,17 +552,6 @@ __global__ void k_extrapolate(int64_t n, double* __restrict__ P, double* __restr
     P[i] = 2.0 * p - Pprev[i];
     Pprev[i] = p;
 }
-// quadratic extrapolation from three time levels: P <- 3 P - 3 Pprev + Pprev2, shifting the history
-__global__ void k_extrapolate2(int64_t n, double* __restrict__ P, double* __restrict__ Pprev,
-                               double* __restrict__ Pprev2) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double p1 = P[i], p2 = Pprev[i], p3 = Pprev2[i];
-    P[i] = 3.0 * (p1 - p2) + p3;
-    Pprev2[i] = p2;
-    Pprev[i] = p1;
-}
-
 __global__ void k_mark_unconverged(int n_members, const int* __restrict__ done, int* __restrict__ cg_fail) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m < n_members && !done[m]) cg_fail[m] = 1;
@@ -632,8 +621,6 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
     HM_CHECK(ctx->ws.get("sim.P", vec, &P));
     double* Pprev;
     HM_CHECK(ctx->ws.get("sim.Pprev", vec, &Pprev));
-    double* Pprev2 = nullptr;
-    if (d.warm_start == 2) HM_CHECK(ctx->ws.get("sim.Pprev2", vec, &Pprev2));
     HM_CHECK(ctx->ws.get("sim.Vxl", vec + (size_t)d.Ny, &Vxl));  // + zero pad, see sat_tile_body
     HM_CHECK(ctx->ws.get("sim.Vyl", vec + 1, &Vyl));
     HM_CHECK(ctx->ws.get("sim.Sa", vec, &Sa));
@@ -713,11 +700,7 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
                                                      TYl, dinv, pin);
         timer.mark(1);
         HM_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(int), st));
-        if (step >= 3 && d.warm_start == 2) {  // P = P_{k-1}, Pprev = P_{k-2}, Pprev2 = P_{k-3}
-            k_extrapolate2<<<copy_blocks, 256, 0, st>>>((int64_t)vec, P, Pprev, Pprev2);
-            ctx->sim_stats.kernel_launches += 1;
-        } else if (step >= 2 && d.warm_start != 1) {  // P holds P_{k-1}, Pprev holds P_{k-2}
-            if (d.warm_start == 2) HM_CUDA(cudaMemcpyAsync(Pprev2, Pprev, vec * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        if (step >= 2 && d.warm_start != 1) {  // P holds P_{k-1}, Pprev holds P_{k-2}
             k_extrapolate<<<copy_blocks, 256, 0, st>>>((int64_t)vec, P, Pprev);
             ctx->sim_stats.kernel_launches += 1;
         } else if (step == 1) {

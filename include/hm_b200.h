@@ -107,8 +107,8 @@ typedef struct hm_sim_desc {
                             * transport kernel (all sub-steps of a time step in one launch) where a member's tiles fit a
                             * thread-block cluster, else the streaming transport kernel.  1 = streamed path, streaming
                             * transport kernel (one sub-step per launch).  2 = streamed path, cluster transport kernel. */
-    int32_t warm_start;    /* initial guess of a pressure solve from the previous time levels: 0 = linear extrapolation
-                            * (default), 1 = previous pressure, 2 = quadratic extrapolation */
+    int32_t warm_start;    /* initial guess of a pressure solve: 0 = linear extrapolation of the two previous pressures
+                            * (default), 1 = the previous pressure (measured: same iteration counts) */
 } hm_sim_desc;
 
 /* statistics of the last hm_sim_batch on this ctx (host side) */
