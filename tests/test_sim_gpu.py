@@ -157,6 +157,27 @@ def test_full_size_properties():
     assert np.abs(res.obs.cpu().numpy()).max() < 1e-12  # no breakthrough yet
 
 
+def test_config_d_size_properties():
+    """BASELINE config D grid (512^2, streaming transport kernel, 3 streamed multigrid levels): invariants."""
+    import torch
+
+    from historymatching_b200.sim import run_ensemble
+
+    m, grid, logk, cells, rates, prd = _setup(512, 512, 2, seed=2)
+    K = torch.as_tensor(orr.perm_transf(logk), device="cuda")
+    dt = 0.025
+    res = run_ensemble(grid, K, cells, rates, torch.zeros(grid.M, dtype=torch.float64, device="cuda"), dt, 1,
+                       obs_cell=prd, want_substeps=True)
+    S = res.S_last.cpu().numpy()
+    assert not res.status.cpu().numpy().any()
+    assert (res.substeps.cpu().numpy() == 9831).all()  # SURVEY.md Appendix A.5
+    assert res.stats["sat_kernel_launches"] == 9831      # one launch per sub-step
+    assert S.min() >= 0 and S.max() < 1
+    vol = S.sum(-1) * (grid.Lx / grid.Nx) * (grid.Ly / grid.Ny)
+    np.testing.assert_allclose(vol, dt, rtol=1e-9)     # water balance before breakthrough
+    assert np.abs(res.obs.cpu().numpy()).max() < 1e-12
+
+
 def test_extreme_contrast_floor(golden):
     """The notebook's own seed-1 prior (HistoryMatch.py:78,290) contains K up to 2.8e8."""
     from historymatching_b200.sim import run_ensemble
