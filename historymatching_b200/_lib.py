@@ -47,7 +47,7 @@ class SimDesc(C.Structure):
 class SimStats(C.Structure):
     _fields_ = [
         ("cg_iterations", i64), ("sat_substeps", i64), ("kernel_launches", i64),
-        ("cg_kernel_launches", i64), ("sat_kernel_launches", i64),
+        ("cg_kernel_launches", i64), ("sat_kernel_launches", i64), ("mg_fp64_fallbacks", i64),
     ]
 
 
@@ -80,6 +80,7 @@ SYMBOLS = {
     "hm_iles_step": (C.c_int, [C.c_void_p, i64, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_double]),
     "hm_iles_recompose": (C.c_int, [C.c_void_p, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hm_corr": (C.c_int, [C.c_void_p, i64, i64, i64, C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, C.c_int]),
 }
 
 _lib = None

@@ -83,6 +83,37 @@ def _is_tensor(x):
     return type(x).__module__.startswith("torch")
 
 
+def _cov_corr(a, b, corr):
+    was_np = not _is_tensor(a)
+    A = _dev(a)
+    B = _dev(b, like=A)
+    N = A.shape[0]
+    A2 = A.reshape(N, -1).contiguous()
+    vec = B.ndim == 1
+    B2 = (B.reshape(N, 1) if vec else B.reshape(N, -1)).contiguous()
+    if B2.shape[0] != N:
+        raise ValueError("a and b must have the same ensemble size (shape[0])")
+    M, q = A2.shape[1], B2.shape[1]
+    torch = _torch()
+    out = torch.empty((M, q), dtype=torch.float64, device=A2.device)
+    ctx = _ctx(A2)
+    _lib.check(ctx.lib.hm_corr(ctx.handle, N, M, q, _p(A2), M, _p(B2), q, _p(out), int(corr)))
+    out = out.reshape(A.shape[1:] + (() if vec else (q,)))
+    return _back(out, was_np)
+
+
+def cov(a, b):
+    """``utils.cov`` (``tools/utils.py:31-39``) on the device: ``center(a).T @ center(b) / (N-1)``."""
+    return _cov_corr(a, b, False)
+
+
+def corr(a, b):
+    """``utils.corr`` (``tools/utils.py:42-55``) on the device, e.g. the correlation field between the
+    permeability ensemble ``a (N,M)`` and one well observation ``b (N,)`` (``HistoryMatch.py:738-748, 829-833``):
+    ``cov / std(a) / std(b)`` (ddof=1), clipped to [-999, 999].  For a 2-D ``b (N,q)`` the result is ``(M,q)``."""
+    return _cov_corr(a, b, True)
+
+
 def ens_update0(prior_ens, obs_ens, obs, perturbs, decorr):
     """ES analysis update; see ``HistoryMatch.py:578-586``."""
     was_np = not _is_tensor(prior_ens)

@@ -615,3 +615,83 @@ extern "C" int hm_iles_recompose(hm_ctx* ctx, int64_t N, int64_t M, const double
     HM_CUDA(cudaGetLastError());
     return HM_OK;
 }
+
+// ---- ensemble covariance / correlation fields (utils.cov / utils.corr, tools/utils.py:31-55) ----------
+// out (M,q) = center(a)^T center(b) / (N-1) [ / std(a) / std(b), clipped to +-999 ].  center(b) has zero
+// column sums, so a itself need not be centred for the product.  Streaming and HBM bound: `a` (N,M) is read
+// twice (two-pass variance, as numpy) by one thread per column, coalesced across columns; the correlated
+// series b is small (q columns, usually 1: the dashboards correlate a field with one well observation,
+// HistoryMatch.py:478-482, 738-748, 829-833) and is read through the read-only path as a warp broadcast.
+namespace {
+
+constexpr int kCorrQ = 8;  // columns of b handled per pass over a
+
+// Bc = center(b) (N,q) dense; sb[t] = sample standard deviation of column t (ddof = 1)
+__global__ void k_corr_prep(int64_t N, int64_t q, const double* __restrict__ b, int64_t ldb,
+                            double* __restrict__ Bc, double* __restrict__ sb) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= q) return;
+    double s = 0.0;
+    for (int64_t i = 0; i < N; ++i) s += b[i * ldb + t];
+    const double mu = s / (double)N;
+    double v = 0.0;
+    for (int64_t i = 0; i < N; ++i) {
+        const double d = b[i * ldb + t] - mu;
+        Bc[i * q + t] = d;
+        v = fma(d, d, v);
+    }
+    sb[t] = sqrt(v / (double)(N - 1));
+}
+
+__global__ void __launch_bounds__(128)
+k_corr_fields(int64_t N, int64_t M, int64_t q, int64_t t0, const double* __restrict__ a, int64_t lda,
+              const double* __restrict__ Bc, const double* __restrict__ sb, double* __restrict__ out,
+              int corr) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    const int nq = (int)min((int64_t)kCorrQ, q - t0);
+    double s = 0.0;
+    for (int64_t i = 0; i < N; ++i) s += a[i * lda + j];
+    const double mu = s / (double)N;
+    double v = 0.0, acc[kCorrQ];
+#pragma unroll
+    for (int t = 0; t < kCorrQ; ++t) acc[t] = 0.0;
+    for (int64_t i = 0; i < N; ++i) {
+        const double d = a[i * lda + j] - mu;
+        v = fma(d, d, v);
+#pragma unroll
+        for (int t = 0; t < kCorrQ; ++t)
+            if (t < nq) acc[t] = fma(d, __ldg(Bc + i * q + t0 + t), acc[t]);
+    }
+    const double sa = sqrt(v / (double)(N - 1));
+#pragma unroll
+    for (int t = 0; t < kCorrQ; ++t) {
+        if (t < nq) {
+            double c = acc[t] / (double)(N - 1);
+            if (corr) {
+                c = c / sa / sb[t0 + t];
+                if (!isnan(c)) c = fmin(fmax(c, -999.0), 999.0);  // 0/0 stays NaN, as with np.clip
+            }
+            out[j * q + t0 + t] = c;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int hm_corr(hm_ctx* ctx, int64_t N, int64_t M, int64_t q, const double* a, int64_t lda,
+                       const double* b, int64_t ldb, double* out, int corr) {
+    HM_REQUIRE(ctx && a && b && out, "null pointer");
+    HM_REQUIRE(N > 1 && M > 0 && q > 0, "need N > 1 members and non-empty a, b");
+    HM_REQUIRE(lda >= M && ldb >= q, "row strides");
+    HM_CUDA(cudaSetDevice(ctx->device));
+    double *Bc, *sb;
+    HM_CHECK(ctx->ws.get("an.corr_Bc", (size_t)(N * q), &Bc));
+    HM_CHECK(ctx->ws.get("an.corr_sb", (size_t)q, &sb));
+    k_corr_prep<<<(unsigned)((q + 63) / 64), 64, 0, ctx->stream>>>(N, q, b, ldb, Bc, sb);
+    for (int64_t t0 = 0; t0 < q; t0 += kCorrQ)
+        k_corr_fields<<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(N, M, q, t0, a, lda, Bc, sb, out, corr);
+    ctx->launches += 1 + (q + kCorrQ - 1) / kCorrQ;
+    HM_CUDA(cudaGetLastError());
+    return HM_OK;
+}

@@ -102,4 +102,5 @@ struct hm_ctx {
     hm_sim_stats sim_stats{};
     int64_t launches = 0;  // kernels of this library launched on the ctx
     double phase_ms[5] = {0, 0, 0, 0, 0};
+    bool mg_force64 = false;  // pressure_solve: the FP32 multigrid cycle converged too slowly in this forward run
 };

@@ -22,6 +22,7 @@
 // CG itself is two more streamed kernels per iteration (k_cg_spmv 48 B/cell,
 // k_cg_update 48 B/cell).  Members converge independently: a per-member `done`
 // flag makes the CTAs of converged members exit at once.
+#include <cstdlib>
 #include <type_traits>
 
 #include "hm_mg_onchip.cuh"
@@ -31,7 +32,6 @@ namespace hmsim {
 namespace {
 
 constexpr int kOnchipCells = 4096;
-constexpr int kOnchipThreads = 1024;
 
 // One grid level.  T is the arithmetic type of the preconditioner (double by default; float is an
 // option - the V-cycle only has to be a good, fixed, symmetric approximation of A^-1 and CG itself
@@ -71,17 +71,107 @@ __device__ __forceinline__ T stencil(const T* xr, int col, int ny, const T* __re
     return y;
 }
 
-// One stencil evaluation per cell of a whole grid row by a warp, handing (col, c, x_c, 1/diag, b, (A x)_c) to
-// `emit`.  NC != 0 (row length 32 NC known at compile time): the operator values of all the lane's cells are
-// loaded first - 6 NC independent global loads in flight per lane - and consumed afterwards; with a runtime
-// row length the loads of one cell are only issued after the previous cell's result is stored, and the
-// kernels stall on L2 latency (the shared-memory footprint leaves almost no L1).  Same arithmetic as stencil().
-template <typename T, typename TB, int NC, bool STAGE, typename F>
+// Vector access helpers: N consecutive elements at a 16-byte aligned address as 128-bit transactions.
+template <int N, typename U>
+__device__ __forceinline__ void ldv(const U* p, U (&v)[N]) {
+    if constexpr (N == 4 && sizeof(U) == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+    } else if constexpr (N == 4 && sizeof(U) == 8) {
+        const double2 t0 = *reinterpret_cast<const double2*>(p), t1 = *reinterpret_cast<const double2*>(p + 2);
+        v[0] = t0.x, v[1] = t0.y, v[2] = t1.x, v[3] = t1.y;
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) v[k] = p[k];
+    }
+}
+template <int N, typename U>
+__device__ __forceinline__ void stv(U* p, const U (&v)[N]) {
+    if constexpr (N == 4 && sizeof(U) == 4) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    } else if constexpr (N == 4 && sizeof(U) == 8) {
+        *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) p[k] = v[k];
+    }
+}
+
+// One stencil evaluation per cell of a whole grid row by a warp.  `emit(n_tag, col, c, xc, dv, bv, y)` receives
+// n = n_tag.value consecutive cells starting at column col / cell c: their iterate, 1/diag, right-hand side and
+// (A x).  Same arithmetic as stencil().
+// NC != 0 (row length 32 NC known at compile time, a multiple of 128): a lane owns groups of FOUR ADJACENT cells
+// (columns 128 g + 4 lane ..+3), so the operator rows, the three iterate rows, 1/diag and the right-hand side are
+// 128-bit loads (7 shared-memory + 4 global load instructions per 4 cells instead of 28 + 16) and the results
+// are stored as vectors: the streamed multigrid kernels were bound by the LSU instruction rate (ncu: 58-66 % LSU
+// pipe, 34-37 % DRAM), not by HBM.  The global loads of a group pair are issued before its shared-memory phase.
+// NC == 0: runtime row length, one cell per lane and step.
+// OPS (FP32, row length 128): the operator rows are staged in shared memory as well (txs / tys, same row layout
+// as ds / bs), so the NU + 1 stencil passes of a tile touch global memory once instead of once per pass.
+template <typename T, typename TB, int NC, bool STAGE, bool OPS, typename F>
 __device__ __forceinline__ void row_stencil(const T* xr, int ny, int lane, int c0, int li0,
                                             const T* __restrict__ TX, const T* __restrict__ TY,
                                             const T* __restrict__ dinv, const TB* __restrict__ b, const T* ds,
-                                            const T* bs, T pinv, F&& emit) {
-    if constexpr (NC != 0) {
+                                            const T* bs, const T* txs, const T* tys, T pinv, F&& emit) {
+    if constexpr (NC != 0 && sizeof(T) == 4) {
+        static_assert(NC % 4 == 0, "row length must be a multiple of 128");
+        constexpr int NG = NC / 4;                                   // groups of 4 cells per lane
+        constexpr int GB = (sizeof(T) == 4 && NG >= 2) ? 2 : 1;     // groups whose loads are in flight together
+#pragma unroll
+        for (int g0 = 0; g0 < NG; g0 += GB) {
+            T tx0[GB][4], tx1[GB][4], ty0[GB][4], tyr[GB], dv[GB][4], bv[GB][4];
+#pragma unroll
+            for (int g = 0; g < GB; ++g) {
+                const int col = 128 * (g0 + g) + 4 * lane, c = c0 + col;
+                if constexpr (OPS) {
+                    ldv<4>(txs + li0 + col, tx0[g]);
+                    ldv<4>(txs + li0 + col + ny, tx1[g]);
+                    ldv<4>(tys + li0 + col, ty0[g]);
+                    tyr[g] = tys[li0 + col + 4];
+                } else {
+                    ldv<4>(TX + c, tx0[g]);
+                    ldv<4>(TX + c + ny, tx1[g]);
+                    ldv<4>(TY + c, ty0[g]);
+                    tyr[g] = TY[c + 4];
+                }
+                if constexpr (STAGE) {
+                    ldv<4>(ds + li0 + col, dv[g]);
+                    ldv<4>(bs + li0 + col, bv[g]);
+                } else {
+                    ldv<4>(dinv + c, dv[g]);
+                    TB bt[4];
+                    ldv<4>(b + c, bt);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) bv[g][k] = (T)bt[k];
+                }
+            }
+            asm volatile("" ::: "memory");  // keep every global load above the shared-memory phase
+#pragma unroll
+            for (int g = 0; g < GB; ++g) {
+                const int col = 128 * (g0 + g) + 4 * lane, c = c0 + col;
+                T xc[4], xu[4], xd[4], y[4];
+                ldv<4>(xr + col, xc);
+                ldv<4>(xr + col - ny, xu);
+                ldv<4>(xr + col + ny, xd);
+                const T xl = xr[col - 1], xh = xr[col + 4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const T lo = k == 0 ? xl : xc[k - 1], hi = k == 3 ? xh : xc[k + 1];
+                    const T tyh = k == 3 ? tyr[g] : ty0[g][k + 1];
+                    T v = tx0[g][k] * (xc[k] - xu[k]);
+                    v = fma(tx1[g][k], xc[k] - xd[k], v);
+                    v = fma(ty0[g][k], xc[k] - lo, v);
+                    v = fma(tyh, xc[k] - hi, v);
+                    if (c + k == 0) v = fma(pinv, xc[k], v);
+                    y[k] = v;
+                }
+                emit(std::integral_constant<int, 4>{}, col, c, xc, dv[g], bv[g], y);
+            }
+        }
+    } else if constexpr (NC != 0) {
+        // FP64: one cell per lane and step (lanes along the row), the operator values of all the lane's cells
+        // loaded first.  (Measured: the 4-adjacent-cells layout needs 60 registers in FP64 and is 14 % slower.)
         T tx0[NC], tx1[NC], ty0[NC], ty1[NC], dv[NC], bv[NC];
 #pragma unroll
         for (int q = 0; q < NC; ++q) {
@@ -97,19 +187,22 @@ __device__ __forceinline__ void row_stencil(const T* xr, int ny, int lane, int c
 #pragma unroll
         for (int q = 0; q < NC; ++q) {
             const int col = lane + 32 * q, c = c0 + col;
-            const T xc = xr[col];
-            T y = tx0[q] * (xc - xr[col - ny]);
-            y = fma(tx1[q], xc - xr[col + ny], y);
-            y = fma(ty0[q], xc - xr[col - 1], y);
-            y = fma(ty1[q], xc - xr[col + 1], y);
-            if (c == 0) y = fma(pinv, xc, y);
-            emit(col, c, xc, dv[q], bv[q], y);
+            const T xc[1] = {xr[col]};
+            T y = tx0[q] * (xc[0] - xr[col - ny]);
+            y = fma(tx1[q], xc[0] - xr[col + ny], y);
+            y = fma(ty0[q], xc[0] - xr[col - 1], y);
+            y = fma(ty1[q], xc[0] - xr[col + 1], y);
+            if (c == 0) y = fma(pinv, xc[0], y);
+            const T dvv[1] = {dv[q]}, bvv[1] = {bv[q]}, yv[1] = {y};
+            emit(std::integral_constant<int, 1>{}, col, c, xc, dvv, bvv, yv);
         }
     } else {
         for (int col = lane; col < ny; col += 32) {
             const int c = c0 + col;
-            const T dvv = STAGE ? ds[li0 + col] : dinv[c], bvv = STAGE ? bs[li0 + col] : (T)b[c];
-            emit(col, c, xr[col], dvv, bvv, stencil<T>(xr, col, ny, TX + c, TY + c, c == 0, pinv));
+            const T xc[1] = {xr[col]};
+            const T dvv[1] = {STAGE ? ds[li0 + col] : dinv[c]}, bvv[1] = {STAGE ? bs[li0 + col] : (T)b[c]};
+            const T y[1] = {stencil<T>(xr, col, ny, TX + c, TY + c, c == 0, pinv)};
+            emit(std::integral_constant<int, 1>{}, col, c, xc, dvv, bvv, y);
         }
     }
 }
@@ -186,19 +279,60 @@ k_mg_down(Lvl<T> f, int cny, T* __restrict__ cb, const double* __restrict__ pin,
     T* xb = sm + L * ny;
     T* bs = sm + 2 * L * ny;
     T* ds = sm + 3 * L * ny;
+    constexpr bool OPS = STAGE && NY == 128;
+    T* txs = sm + 4 * L * ny;       // L + 1 rows: local row lr <-> low x-faces of grid row r0 - H + lr
+    T* tys = txs + (L + 1) * ny;    // L rows + 4 zeros
+    if constexpr (OPS) {
+        for (int lr = warp; lr < L + 1; lr += nW) {
+            const int row = r0 - H + lr;
+            const int col = 4 * lane;
+            T tx[4] = {0, 0, 0, 0}, ty[4] = {0, 0, 0, 0};
+            // row == nx reads the zero pad / the (zero) low faces of the next member's first row
+            if (row >= 0 && row <= f.nx) ldv<4>(TX + row * ny + col, tx);
+            if (row >= 0 && row < f.nx && lr < L) ldv<4>(TY + row * ny + col, ty);
+            stv<4>(txs + lr * ny + col, tx);
+            if (lr < L) stv<4>(tys + lr * ny + col, ty);
+            else if (lane == 0) stv<4>(tys + L * ny, ty);
+        }
+    }
     for (int lr = warp; lr < rows + 2 * H; lr += nW) {
         const int row = r0 - H + lr;
         const bool in = row >= 0 && row < f.nx;
         const int c0 = row * ny;
+        if constexpr (NY != 0 && sizeof(T) == 4) {  // FP32: 4 adjacent cells per lane, 128-bit loads / stores
 #pragma unroll
-        for (int col = lane; col < ny; col += 32) {
-            const T bv = in ? (T)b[c0 + col] : (T)0, dv = in ? dinv[c0 + col] : (T)0;
-            if (STAGE) {
-                bs[lr * ny + col] = bv;
-                ds[lr * ny + col] = dv;
+            for (int g = 0; g < NY / 128; ++g) {
+                const int col = 128 * g + 4 * lane;
+                TB bt[4] = {0, 0, 0, 0};
+                T bv[4], dv[4] = {0, 0, 0, 0}, x0[4];
+                const T zero[4] = {0, 0, 0, 0};
+                if (in) {
+                    ldv<4>(b + c0 + col, bt);
+                    ldv<4>(dinv + c0 + col, dv);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    bv[k] = (T)bt[k];
+                    x0[k] = (T)cheb_w(0) * dv[k] * bv[k];
+                }
+                if (STAGE) {
+                    stv<4>(bs + lr * ny + col, bv);
+                    stv<4>(ds + lr * ny + col, dv);
+                }
+                stv<4>(xa + lr * ny + col, x0);
+                stv<4>(xb + lr * ny + col, zero);
             }
-            xa[lr * ny + col] = (T)cheb_w(0) * dv * bv;
-            xb[lr * ny + col] = (T)0;
+        } else {
+#pragma unroll
+            for (int col = lane; col < ny; col += 32) {
+                const T bv = in ? (T)b[c0 + col] : (T)0, dv = in ? dinv[c0 + col] : (T)0;
+                if (STAGE) {
+                    bs[lr * ny + col] = bv;
+                    ds[lr * ny + col] = dv;
+                }
+                xa[lr * ny + col] = (T)cheb_w(0) * dv * bv;
+                xb[lr * ny + col] = (T)0;
+            }
         }
     }
     __syncthreads();
@@ -211,8 +345,15 @@ k_mg_down(Lvl<T> f, int cny, T* __restrict__ cb, const double* __restrict__ pin,
             const int c0 = row * ny;
             const T* xr = xa + lr * ny;
             T* xo = xb + lr * ny;
-            row_stencil<T, TB, NY / 32, STAGE>(xr, ny, lane, c0, lr * ny, TX, TY, dinv, b, ds, bs, pinv,
-                                               [&](int col, int, T xc, T dv, T bv, T y) { xo[col] = xc + w * dv * (bv - y); });
+            row_stencil<T, TB, NY / 32, STAGE, OPS>(xr, ny, lane, c0, lr * ny, TX, TY, dinv, b, ds, bs, txs, tys, pinv,
+                                               [&](auto n, int col, int, const auto& xc, const auto& dv, const auto& bv,
+                                                   const auto& y) {
+                                                   constexpr int NV = decltype(n)::value;
+                                                   T o[NV];
+#pragma unroll
+                                                   for (int k = 0; k < NV; ++k) o[k] = xc[k] + w * dv[k] * (bv[k] - y[k]);
+                                                   stv<NV>(xo + col, o);
+                                               });
         }
         __syncthreads();
         T* tsw = xa;
@@ -225,10 +366,15 @@ k_mg_down(Lvl<T> f, int cny, T* __restrict__ cb, const double* __restrict__ pin,
         const T* xr = xa + (lr + H) * ny;
         T* xo = xb + lr * ny;
         T* xg = f.xa + off;
-        row_stencil<T, TB, NY / 32, STAGE>(xr, ny, lane, c0, (lr + H) * ny, TX, TY, dinv, b, ds, bs, pinv,
-                                           [&](int col, int c, T xc, T, T bv, T y) {
-                                               xg[c] = xc;
-                                               xo[col] = bv - y;
+        row_stencil<T, TB, NY / 32, STAGE, OPS>(xr, ny, lane, c0, (lr + H) * ny, TX, TY, dinv, b, ds, bs, txs, tys, pinv,
+                                           [&](auto n, int col, int c, const auto& xc, const auto&, const auto& bv,
+                                               const auto& y) {
+                                               constexpr int NV = decltype(n)::value;
+                                               T o[NV], xv[NV];
+#pragma unroll
+                                               for (int k = 0; k < NV; ++k) o[k] = bv[k] - y[k], xv[k] = xc[k];
+                                               stv<NV>(xg + c, xv);
+                                               stv<NV>(xo + col, o);
                                            });
     }
     __syncthreads();
@@ -284,19 +430,63 @@ k_mg_up(Lvl<T> f, int cny, const T* __restrict__ cx, const double* __restrict__ 
     T* xb = sm + L * ny;
     T* bs = sm + 2 * L * ny;
     T* ds = sm + 3 * L * ny;
+    constexpr bool OPS = STAGE && NY == 128;
+    T* txs = sm + 4 * L * ny;       // L + 1 rows: local row lr <-> low x-faces of grid row r0 - H + lr
+    T* tys = txs + (L + 1) * ny;    // L rows + 4 zeros
+    if constexpr (OPS) {
+        for (int lr = warp; lr < L + 1; lr += nW) {
+            const int row = r0 - H + lr;
+            const int col = 4 * lane;
+            T tx[4] = {0, 0, 0, 0}, ty[4] = {0, 0, 0, 0};
+            // row == nx reads the zero pad / the (zero) low faces of the next member's first row
+            if (row >= 0 && row <= f.nx) ldv<4>(TX + row * ny + col, tx);
+            if (row >= 0 && row < f.nx && lr < L) ldv<4>(TY + row * ny + col, ty);
+            stv<4>(txs + lr * ny + col, tx);
+            if (lr < L) stv<4>(tys + lr * ny + col, ty);
+            else if (lane == 0) stv<4>(tys + L * ny, ty);
+        }
+    }
     for (int lr = warp; lr < rows + 2 * H; lr += nW) {
         const int row = r0 - H + lr;
         const bool in = row >= 0 && row < f.nx;
         const int c0 = row * ny;
         const T* xcr = xc + (row >> 1) * cny;
+        if constexpr (NY != 0 && sizeof(T) == 4) {  // FP32: 4 adjacent cells per lane, 128-bit loads / stores
 #pragma unroll
-        for (int col = lane; col < ny; col += 32) {
-            if (STAGE) {
-                bs[lr * ny + col] = in ? (T)b[c0 + col] : (T)0;
-                ds[lr * ny + col] = in ? dinv[c0 + col] : (T)0;
+            for (int g = 0; g < NY / 128; ++g) {
+                const int col = 128 * g + 4 * lane;
+                T x0[4] = {0, 0, 0, 0};
+                const T zero[4] = {0, 0, 0, 0};
+                if (in) {
+                    ldv<4>(xin + c0 + col, x0);
+                    const T ca = xcr[col >> 1], cb2 = xcr[(col >> 1) + 1];
+                    x0[0] += ca, x0[1] += ca, x0[2] += cb2, x0[3] += cb2;
+                }
+                if (STAGE) {
+                    TB bt[4] = {0, 0, 0, 0};
+                    T bv[4], dv[4] = {0, 0, 0, 0};
+                    if (in) {
+                        ldv<4>(b + c0 + col, bt);
+                        ldv<4>(dinv + c0 + col, dv);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) bv[k] = (T)bt[k];
+                    stv<4>(bs + lr * ny + col, bv);
+                    stv<4>(ds + lr * ny + col, dv);
+                }
+                stv<4>(xa + lr * ny + col, x0);
+                stv<4>(xb + lr * ny + col, zero);
             }
-            xa[lr * ny + col] = in ? xin[c0 + col] + xcr[col >> 1] : (T)0;
-            xb[lr * ny + col] = (T)0;
+        } else {
+#pragma unroll
+            for (int col = lane; col < ny; col += 32) {
+                if (STAGE) {
+                    bs[lr * ny + col] = in ? (T)b[c0 + col] : (T)0;
+                    ds[lr * ny + col] = in ? dinv[c0 + col] : (T)0;
+                }
+                xa[lr * ny + col] = in ? xin[c0 + col] + xcr[col >> 1] : (T)0;
+                xb[lr * ny + col] = (T)0;
+            }
         }
     }
     __syncthreads();
@@ -309,8 +499,15 @@ k_mg_up(Lvl<T> f, int cny, const T* __restrict__ cx, const double* __restrict__ 
             const int c0 = row * ny;
             const T* xr = xa + lr * ny;
             T* xo = xb + lr * ny;
-            row_stencil<T, TB, NY / 32, STAGE>(xr, ny, lane, c0, lr * ny, TX, TY, dinv, b, ds, bs, pinv,
-                                               [&](int col, int, T xc, T dv, T bv, T y) { xo[col] = xc + w * dv * (bv - y); });
+            row_stencil<T, TB, NY / 32, STAGE, OPS>(xr, ny, lane, c0, lr * ny, TX, TY, dinv, b, ds, bs, txs, tys, pinv,
+                                               [&](auto n, int col, int, const auto& xc, const auto& dv, const auto& bv,
+                                                   const auto& y) {
+                                                   constexpr int NV = decltype(n)::value;
+                                                   T o[NV];
+#pragma unroll
+                                                   for (int k = 0; k < NV; ++k) o[k] = xc[k] + w * dv[k] * (bv[k] - y[k]);
+                                                   stv<NV>(xo + col, o);
+                                               });
         }
         __syncthreads();
         T* tsw = xa;
@@ -321,11 +518,18 @@ k_mg_up(Lvl<T> f, int cny, const T* __restrict__ cx, const double* __restrict__ 
     for (int lr = warp; lr < rows; lr += nW) {
         const int c0 = (r0 + lr) * ny;
         const T* xr = xa + (lr + H) * ny;
-        row_stencil<T, TB, NY / 32, STAGE>(xr, ny, lane, c0, (lr + H) * ny, TX, TY, dinv, b, ds, bs, pinv,
-                                           [&](int, int c, T xc, T dv, T bv, T y) {
-                                               const T v = xc + (T)cheb_w(0) * dv * (bv - y);
-                                               xout[c] = (TB)v;
-                                               if (TOP) dot = fma((double)bv, (double)v, dot);
+        row_stencil<T, TB, NY / 32, STAGE, OPS>(xr, ny, lane, c0, (lr + H) * ny, TX, TY, dinv, b, ds, bs, txs, tys, pinv,
+                                           [&](auto n, int, int c, const auto& xc, const auto& dv, const auto& bv,
+                                               const auto& y) {
+                                               constexpr int NV = decltype(n)::value;
+                                               TB o[NV];
+#pragma unroll
+                                               for (int k = 0; k < NV; ++k) {
+                                                   const T v = xc[k] + (T)cheb_w(0) * dv[k] * (bv[k] - y[k]);
+                                                   o[k] = (TB)v;
+                                                   if (TOP) dot = fma((double)bv[k], (double)v, dot);
+                                               }
+                                               stv<NV>(xout + c, o);
                                            });
     }
     if (TOP) {
@@ -352,17 +556,26 @@ k_mg_dense_inverse(int nm, int n, int nx, int ny, const T* __restrict__ TX, cons
 
 // One CTA per member runs the cycle (V, or W on the levels of at least `wmin` cells) on the shared-memory
 // hierarchy; the coarsest level (<= 32 cells) is solved exactly with the precomputed dense inverse.
+// FP64: 1024 threads, one CTA per SM (the hierarchy fills the shared memory).  FP32: the hierarchy is half the
+// size, so two 512-thread CTAs (two members) share an SM and fill each other's barrier bubbles.
 template <typename T>
-__global__ void __launch_bounds__(kOnchipThreads, 1)
+struct OnchipCfg {
+    static constexpr int NT = sizeof(T) == 4 ? 512 : 1024;
+    static constexpr int CTAS = sizeof(T) == 4 ? 2 : 1;
+};
+template <typename T>
+__global__ void __launch_bounds__(OnchipCfg<T>::NT, OnchipCfg<T>::CTAS)
 k_mg_onchip(const __grid_constant__ OnchipMeta mt, const T* __restrict__ b_in, T* __restrict__ x_out,
-            const double* __restrict__ pin, const int* __restrict__ done, const double* __restrict__ Ainv_g) {
+            const double* __restrict__ pin, const int* __restrict__ done, const double* __restrict__ Ainv_g,
+            int ainv_off /* bytes from the start of the dynamic shared memory, 8-aligned */) {
+    constexpr int NT = OnchipCfg<T>::NT;
     T* sm = smem_as<T>();
-    __shared__ double Ainv[kDenseMax * kDenseMax];
+    double* Ainv = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sm) + ainv_off);
     const int m = blockIdx.x;
     if (done[m]) return;
     {
         const int nn = mt.M[mt.n - 1] * mt.M[mt.n - 1];
-        for (int e = threadIdx.x; e < nn; e += kOnchipThreads) Ainv[e] = Ainv_g[(int64_t)m * nn + e];
+        for (int e = threadIdx.x; e < nn; e += NT) Ainv[e] = Ainv_g[(int64_t)m * nn + e];
     }
     OnchipSmem<T> s;
     s.X = sm;
@@ -375,21 +588,21 @@ k_mg_onchip(const __grid_constant__ OnchipMeta mt, const T* __restrict__ b_in, T
         const T* tx = static_cast<const T*>(mt.TX[l]) + g;
         const T* ty = static_cast<const T*>(mt.TY[l]) + g;
         const T* dv = static_cast<const T*>(mt.dinv[l]) + g;
-        for (int e = threadIdx.x; e < mt.M[l]; e += kOnchipThreads) {
+        for (int e = threadIdx.x; e < mt.M[l]; e += NT) {
             s.TX[mt.off[l] + e] = tx[e];
             s.TY[mt.off[l] + e] = ty[e];
             s.DV[mt.off[l] + e] = dv[e];
         }
     }
     const int M0 = mt.M[0];
-    for (int e = threadIdx.x; e < M0; e += kOnchipThreads) {
+    for (int e = threadIdx.x; e < M0; e += NT) {
         s.B[e] = b_in[(int64_t)m * M0 + e];
         s.X[e] = 0;
     }
     __syncthreads();
     const T pinv = (T)pin[m];
-    onchip_cycle<T, kOnchipThreads, kOnchipCells / kOnchipThreads>(mt, s, pinv, 0, Ainv);
-    for (int e = threadIdx.x; e < M0; e += kOnchipThreads) x_out[(int64_t)m * M0 + e] = s.X[e];
+    onchip_cycle<T, NT, kOnchipCells / NT>(mt, s, pinv, 0, Ainv);
+    for (int e = threadIdx.x; e < M0; e += NT) x_out[(int64_t)m * M0 + e] = s.X[e];
 }
 
 // ---- CG kernels -------------------------------------------------------------------------------
@@ -584,13 +797,18 @@ struct MgHierarchy {
     int nLev = 0, firstOn = 0, nm = 0;
     OnchipMeta mt{};
     size_t smemOn = 0;
+    int ainvOff = 0;
     const double* pin = nullptr;
     int* done = nullptr;
     double* part_rz = nullptr;
     size_t nPart = 0;
     double* Ainv = nullptr;  // [member][n][n]: dense inverse (FP64) of the coarsest level
 
-    size_t smem_level(int l) const { return (size_t)(sizeof(T) == 4 ? 4 : 2) * (lv[l].R + 2 * kNu) * lv[l].ny * sizeof(T); }
+    size_t smem_level(int l) const {
+        const size_t L = (size_t)lv[l].R + 2 * kNu, ny = (size_t)lv[l].ny;
+        if (sizeof(T) == 4 && l == 0 && ny == 128) return (6 * L * ny + ny + 4) * sizeof(T);  // + staged operator rows
+        return (size_t)(sizeof(T) == 4 ? 4 : 2) * L * ny * sizeof(T);
+    }
 
     int build(hm_ctx* ctx, const Geo& g, int nm_, const double* TXl, const double* TYl, const double* dinv,
               const double* pin_, double* Rv, double* Z, bool wcycle, int* done_, double* part_rz_, size_t nPart_) {
@@ -685,7 +903,8 @@ struct MgHierarchy {
         }
         mt.total = o;
         mt.wmin = wcycle ? kWcycleMinCells : 0x7fffffff;
-        smemOn = (size_t)5 * o * sizeof(T);
+        ainvOff = (int)((((size_t)5 * o * sizeof(T)) + 7) & ~(size_t)7);
+        smemOn = (size_t)ainvOff + (size_t)lv[nLev - 1].M * lv[nLev - 1].M * sizeof(double);
         HM_CUDA(cudaFuncSetAttribute(k_mg_onchip<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemOn));
         {   // dense inverse of the coarsest level, one warp per member
             const Lvl<T>& L = lv[nLev - 1];
@@ -728,8 +947,8 @@ struct MgHierarchy {
             else
                 k_mg_down<T, false><<<grid, kThreads, sm, st>>>(lv[l], lv[l + 1].ny, cb, pin, done);
         }
-        k_mg_onchip<T><<<nm, kOnchipThreads, smemOn, st>>>(mt, static_cast<const T*>(lv[firstOn].b),
-                                                            static_cast<T*>(lv[firstOn].xb), pin, done, Ainv);
+        k_mg_onchip<T><<<nm, OnchipCfg<T>::NT, smemOn, st>>>(mt, static_cast<const T*>(lv[firstOn].b),
+                                                              static_cast<T*>(lv[firstOn].xb), pin, done, Ainv, ainvOff);
         for (int l = firstOn - 1; l >= 0; --l) {
             const T* cx = static_cast<const T*>(lv[l + 1].xb);
             const int grid = nm * lv[l].nTiles;
@@ -784,10 +1003,22 @@ int pressure_solve(hm_ctx* ctx, const Geo& g, const Wells& w, int step, int nm, 
         HM_CUDA(cudaFuncSetAttribute(k_cg_spmv<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     }
 
-    // ---- multigrid hierarchy: FP64 V-cycle (precond 0), FP64 W-cycle (2) or FP32 V-cycle (3) ------------
+    // ---- multigrid hierarchy --------------------------------------------------------------------------
+    // precond 0 (default): V-cycle in FP32 arithmetic (operators, smoothing and transfers; CG itself, its
+    // operator and the convergence test stay FP64, so the solution meets the same tolerance).  The cycle only
+    // has to be a fixed SPD approximation of A^-1: on smooth log-normal fields FP32 costs ~3 % more iterations
+    // at ~70 % of the time per iteration (measured at 128^2 x 1024: 104 vs 141 ms per 8 solves).  Fields that
+    // need many iterations (rough, high contrast) lose more to the rounding noise of the cycle, so a solve that
+    // has not converged after kSwitchIters iterations (twice that for the cold first solve of a run, which
+    // starts from P = 0) restarts CG (beta = 0) with the FP64 cycle; when that happens on a warm-started solve
+    // the rest of the forward run stays FP64 (ctx->mg_force64).  precond 4 = FP64 V-cycle, 2 = FP64 W-cycle,
+    // 3 = FP32 V-cycle without fallback.
+    int kSwitchIters = step == 0 ? 80 : 40;
+    if (const char* e = getenv("HM_MG_SWITCH_ITERS")) kSwitchIters = std::max(1, atoi(e));  // test hook
     MgHierarchy<float> mgf;
     MgHierarchy<double> mgd;
-    const bool mg32 = precond == 3;
+    const bool adaptive = precond == 0;
+    bool mg32 = precond == 3 || (adaptive && !ctx->mg_force64);
     if (!jacobi) {
         if (mg32)
             HM_CHECK(mgf.build(ctx, g, nm, TXl, TYl, dinv, pin, Rv, Z, false, done, part_rz, nPart));
@@ -814,6 +1045,7 @@ int pressure_solve(hm_ctx* ctx, const Geo& g, const Wells& w, int step, int nm, 
 
     int k = 0;
     bool all_done = false;
+    bool restart = false;  // the next iteration starts a new Krylov space (preconditioner changed): p = z
     const int chk_blocks = (nm + 127) / 128;
     while (k < max_iter && !all_done) {
         const int kend = std::min(max_iter, k + *cg_batch);
@@ -824,8 +1056,9 @@ int pressure_solve(hm_ctx* ctx, const Geo& g, const Wells& w, int step, int nm, 
             k_cg_check<<<chk_blocks, 128, 0, st>>>(nm, g.nTiles, k, tol2, part_rr, bb, done, iters, counters);
             if (!jacobi) precondition(cur);
             auto spmv = g.Ny == 128 ? k_cg_spmv<128> : g.Ny == 512 ? k_cg_spmv<512> : k_cg_spmv<0>;
-            spmv<<<grid, kThreads, smem1, st>>>(g, k, Z, Pin, Pout, AP, TXl, TYl, pin, part_rz + cur * nPart,
-                                                part_rz + nxt * nPart, part_pAp, done);
+            spmv<<<grid, kThreads, smem1, st>>>(g, restart ? 0 : k, Z, Pin, Pout, AP, TXl, TYl, pin,
+                                                part_rz + cur * nPart, part_rz + nxt * nPart, part_pAp, done);
+            restart = false;
             if (jacobi)
                 k_cg_update<true><<<grid, kThreads, 0, st>>>(g, P, Rv, Z, Pout, AP, dinv, part_rz + cur * nPart,
                                                               part_pAp, part_rz + nxt * nPart, part_rr, done);
@@ -836,6 +1069,13 @@ int pressure_solve(hm_ctx* ctx, const Geo& g, const Wells& w, int step, int nm, 
         HM_CUDA(cudaMemcpyAsync(ctx->h_pinned, counters, sizeof(int), cudaMemcpyDeviceToHost, st));
         HM_CUDA(cudaStreamSynchronize(st));
         all_done = ctx->h_pinned[0] >= nm;
+        if (!all_done && adaptive && mg32 && !jacobi && k >= kSwitchIters) {
+            HM_CHECK(mgd.build(ctx, g, nm, TXl, TYl, dinv, pin, Rv, Z, false, done, part_rz, nPart));
+            mg32 = false;
+            restart = true;
+            if (step > 0 || getenv("HM_MG_SWITCH_ITERS")) ctx->mg_force64 = true;
+            ctx->sim_stats.mg_fp64_fallbacks += 1;
+        }
     }
     // the last update may have converged: one more test so that `done` is final
     k_cg_check<<<chk_blocks, 128, 0, st>>>(nm, g.nTiles, k, tol2, part_rr, bb, done, iters, counters);

@@ -21,6 +21,7 @@
 //   k_sat_substep  read S,Vxl,Vyl      write S'                  32 B / sub-step
 #include <cooperative_groups.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "hm_sim_common.cuh"
@@ -288,8 +289,128 @@ __device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uin
                  "l"(__double_as_longlong(v)), "r"(remote_bar) : "memory");
 }
 
+// ---- K4c: streaming sub-step with bulk-copy (TMA) staging -------------------------------------------------
+// Same arithmetic and traffic as k_sat_substep, different data movement.  k_sat_substep is bound by memory
+// latency (ncu at 512^2: long-scoreboard stalls, 48 % of the DRAM peak): a thread first waits for its S values,
+// and issues the flux loads only after the fw barrier.  Here ONE thread issues three bulk copies
+// (cp.async.bulk, completion on an mbarrier) for everything the tile needs - the S rows incl. the two halo rows,
+// the x-fluxes of R+1 rows, the y-fluxes (+ one element) - ~61 KB in flight per CTA, three CTAs per SM; the
+// CTA then turns S into fw(S) in place (own cells keep S in registers), and applies the stencil from shared
+// memory.  Needs an even row length (16-byte granularity of the bulk copies).
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+constexpr int kStreamThreads = 512;
+constexpr int kStreamCPT = kTileCells / kStreamThreads;
+
+template <bool HAS_POR>
+__global__ void __launch_bounds__(kStreamThreads, 3)
+k_sat_stream(Geo g, Fluid fl, Wells w, int step, int it, double dt, const int* __restrict__ nts,
+             const double* __restrict__ Sin, double* __restrict__ Sout, const double* __restrict__ Vxl,
+             const double* __restrict__ Vyl, const double* __restrict__ por) {
+    extern __shared__ __align__(16) double sms[];  // fw/S rows [(R+2) Ny], Vx rows [(R+1) Ny], Vy [R Ny + 2]
+    __shared__ __align__(8) unsigned long long bar_store;
+    __shared__ int wc[kMaxWells];
+    __shared__ double wr[kMaxWells];
+    constexpr int NT = kStreamThreads;
+    const int m = blockIdx.x / g.nTiles, t = blockIdx.x % g.nTiles;
+    const int r0 = t * g.R, r1 = min(r0 + g.R, g.Nx), rows = r1 - r0;
+    const int Ny = g.Ny, nInt = rows * Ny;
+    const int64_t mbase = (int64_t)m * g.M;
+    const int64_t base = mbase + (int64_t)r0 * Ny;  // first interior cell
+    const int n = nts[m];
+    if (it >= n) {  // this member needs fewer sub-steps: carry its state over
+        for (int e = threadIdx.x; e < nInt; e += NT) Sout[base + e] = Sin[base + e];
+        return;
+    }
+    double* Ss = sms;
+    double* Vxs = sms + (g.R + 2) * Ny;
+    double* Vys = Vxs + (g.R + 1) * Ny;
+    const uint32_t bar = smem_u32(&bar_store);
+    if (threadIdx.x == 0) {  // the copies start at once; the other threads meet the barrier after the CTA barrier below
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int rowLo = max(r0 - 1, 0), rowHi = min(r1 + 1, g.Nx);
+        const uint32_t bS = (uint32_t)(rowHi - rowLo) * Ny * 8u, bX = (uint32_t)(rows + 1) * Ny * 8u,
+                       bY = (uint32_t)(nInt + 2) * 8u;
+        mbar_expect_tx(bar, (int)(bS + bX + bY));
+        bulk_g2s(smem_u32(Ss + (rowLo - (r0 - 1)) * Ny), Sin + mbase + (int64_t)rowLo * Ny, bS, bar);
+        bulk_g2s(smem_u32(Vxs), Vxl + base, bX, bar);
+        bulk_g2s(smem_u32(Vys), Vyl + base, bY, bar);
+    }
+    if (w.n > 0) load_wells(w, m, step, wc, wr);
+    // halo rows outside the domain: zero (the matching flux is zero, the value only has to be finite); the bulk
+    // copies do not touch these rows
+    if (t == 0)
+        for (int e = threadIdx.x; e < Ny; e += NT) Ss[e] = 0.0;
+    if (r1 == g.Nx)
+        for (int e = threadIdx.x; e < Ny; e += NT) Ss[(rows + 1) * Ny + e] = 0.0;
+    const double dts = dt / (double)n;
+    const double hdt0 = 0.5 * (dts / g.h2);
+    // one warp polls the mbarrier (512 spinning threads cost ~60 % of the issue slots, ncu), the others sleep in
+    // the CTA barrier; the second wait returns at once and is each thread's own acquire of the copied data
+    if (threadIdx.x < 32) mbar_wait(bar, 0);
+    __syncthreads();
+    mbar_wait(bar, 0);
+    // S -> fw(S) in place; a thread keeps the saturation of its own cells
+    double s[kStreamCPT];
+    double* fwp = Ss + Ny + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < kStreamCPT; ++j) {
+        s[j] = 0.0;
+        if (threadIdx.x + j * NT < nInt) {
+            s[j] = fwp[j * NT];
+            fwp[j * NT] = frac_flow_fast(s[j], fl);
+        }
+    }
+    for (int e = threadIdx.x; e < 2 * Ny; e += NT) {
+        const bool lowh = e < Ny;
+        const int col = lowh ? e : e - Ny;
+        if (lowh ? t > 0 : r1 < g.Nx) {
+            double* q = Ss + (lowh ? col : (rows + 1) * Ny + col);
+            *q = frac_flow_fast(*q, fl);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kStreamCPT; ++j) {
+        const int e = threadIdx.x + j * NT;
+        if (e < nInt) {
+            const double vxl = Vxs[e], vyl = Vys[e], vxh = Vxs[e + Ny], vyh = Vys[e + 1];
+            double hdt = hdt0;
+            if (HAS_POR) hdt = 0.5 * (dts / (g.h2 * por[(int64_t)r0 * Ny + e]));
+            const double* f = fwp + j * NT;
+            // same expression tree as sat_tile_body
+            double acc = (hdt * (vxl + fabs(vxl))) * f[-Ny];
+            acc = fma(hdt * (vyl + fabs(vyl)), f[-1], acc);
+            const double dg = ((vyl - vyh) + (vxl - vxh)) - ((fabs(vyl) + fabs(vyh)) + (fabs(vxl) + fabs(vxh)));
+            acc = fma(hdt * dg, f[0], acc);
+            acc = fma(hdt * (fabs(vyh) - vyh), f[1], acc);
+            acc = fma(hdt * (fabs(vxh) - vxh), f[Ny], acc);
+            Sout[base + e] = s[j] + acc;
+        }
+    }
+    if (w.n == 0) return;
+    __syncthreads();
+    // well fix-up: S += dtx * (min(q,0) * fw(S) + max(q,0)) on the cells that hold wells
+    for (int i = threadIdx.x; i < w.n; i += NT) {
+        const int c = wc[i];
+        const int e = c - r0 * Ny;
+        if (e < 0 || e >= nInt) continue;
+        bool first = true;
+        for (int k = 0; k < i; ++k) first = first && (wc[k] != c);
+        if (!first) continue;
+        const double q = cell_source(c, w.n, wc, wr);
+        double dtx = dts / g.h2;
+        if (HAS_POR) dtx = dts / (g.h2 * por[c]);
+        Sout[base + e] += fma(dtx * fmin(q, 0.0), Ss[Ny + e], fmax(q, 0.0) * dtx);
+    }
+}
+
 template <bool HAS_POR, int NT, int CPT, int NY>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, NT <= 512 ? 2 : 1)
 k_sat_cluster(Geo g, Fluid fl, Wells w, int step, double dt, const int* __restrict__ nts,
               const double* __restrict__ Sin, double* __restrict__ Sout, const double* __restrict__ Vxl,
               const double* __restrict__ Vyl, const double* __restrict__ por) {
@@ -405,6 +526,10 @@ k_sat_cluster(Geo g, Fluid fl, Wells w, int step, double dt, const int* __restri
         const uint32_t colb = 8u * (uint32_t)col;
         const bool unit = fl.inv_range == 1.0 && fl.swc_ir == 0.0 && fl.mr == 1.0;
         const bool lead = threadIdx.x < 32;  // warp-uniform: only warp 0 runs the expect_tx branch
+        bool anySrc = false;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) anySrc = anySrc || sr[j] != 0.0;
+        const bool warpSrc = __any_sync(0xffffffffu, anySrc);
         auto substep = [&](auto unit_tag, double* __restrict__ fw, uint32_t mybar, uint32_t upA, uint32_t upB,
                            uint32_t dnA, uint32_t dnB, int parity) {
             constexpr bool U = decltype(unit_tag)::value;
@@ -422,7 +547,7 @@ k_sat_cluster(Geo g, Fluid fl, Wells w, int step, double dt, const int* __restri
             double acc[CPT];  // the terms that only need this thread's registers, before the barrier
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
-                acc[j] = fma(dg[j], f[j], sr[j]);
+                acc[j] = fma(dg[j], f[j], s[j]);
                 if (j > 0) acc[j] = fma(aW[j], f[j - 1], acc[j]);
                 if (j < CPT - 1) acc[j] = fma(aE[j], f[j + 1], acc[j]);
             }
@@ -441,7 +566,14 @@ k_sat_cluster(Geo g, Fluid fl, Wells w, int step, double dt, const int* __restri
                 a2 = fma(aN[j], fN[j], a2);
                 if (j == 0) a2 = fma(aW[j], fWest, a2);
                 if (j == CPT - 1) a2 = fma(aE[j], fEast, a2);
-                s[j] += a2;
+                s[j] = a2;
+            }
+            if (warpSrc) {  // warp-uniform branch (kept a branch by the opaque asm): only warps holding an injector cell
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    asm volatile("" : "+d"(s[j]));
+                    s[j] += sr[j];
+                }
             }
         };
         double* const fwa = fwb0 + Ny + e0;
@@ -622,7 +754,7 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
     double* Pprev;
     HM_CHECK(ctx->ws.get("sim.Pprev", vec, &Pprev));
     HM_CHECK(ctx->ws.get("sim.Vxl", vec + (size_t)d.Ny, &Vxl));  // + zero pad, see sat_tile_body
-    HM_CHECK(ctx->ws.get("sim.Vyl", vec + 1, &Vyl));
+    HM_CHECK(ctx->ws.get("sim.Vyl", vec + 2, &Vyl));  // + 2: k_sat_stream copies nInt + 2 elements
     HM_CHECK(ctx->ws.get("sim.Sa", vec, &Sa));
     HM_CHECK(ctx->ws.get("sim.Sb", vec, &Sb));
     HM_CHECK(ctx->ws.get("sim.part_pm", nPart, &part_pm));
@@ -666,16 +798,39 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
     // (sat_block != 1).  Tile = 2048 cells = 1024 threads x 2 cells; measured alternatives at 128^2 x 1024 members:
     // 512 threads x 4 cells the same speed, 4096-cell tiles (512 x 8, clusters of 4) spill and are 25 % slower.
     // Row length 128 / 64 is a compile-time constant (immediate shared-memory offsets), other lengths are runtime.
-    const Geo gc = g;
-    const bool use_cluster = d.sat_block != 1 && gc.nTiles <= 16;
-    const int cluster_threads = 1024;
+    // sat_block 4: tiles of 1024 cells, 512 threads, two CTAs (of different members) per SM: the per-sub-step barriers
+    // of the two CTAs are decoupled, so one fills the other's pipeline bubbles.
+    Geo gc = g;
+    const bool half_tiles = d.sat_block == 4 && d.Ny <= 512 && (1024 / d.Ny) >= 2 && d.Nx % (1024 / d.Ny) == 0;
+    if (half_tiles) {
+        gc.R = 1024 / d.Ny;
+        gc.nTiles = d.Nx / gc.R;
+    }
+    const bool use_cluster = d.sat_block != 1 && d.sat_block != 5 && gc.nTiles <= 16;
+    const int cluster_threads = half_tiles ? 512 : 1024;
     const size_t smem_cluster = ((size_t)2 * (gc.R + 2) * d.Ny + (size_t)gc.R * d.Ny) * sizeof(double);
-    auto cluster_kernel = d.por ? k_sat_cluster<true, 1024, 2, 0> : k_sat_cluster<false, 1024, 2, 0>;
+    using cluster_fn = void (*)(Geo, Fluid, Wells, int, double, const int*, const double*, double*, const double*,
+                                const double*, const double*);
+    cluster_fn cluster_kernel = d.por ? k_sat_cluster<true, 1024, 2, 0> : k_sat_cluster<false, 1024, 2, 0>;
     if (d.Ny == 128) cluster_kernel = d.por ? k_sat_cluster<true, 1024, 2, 128> : k_sat_cluster<false, 1024, 2, 128>;
     if (d.Ny == 64) cluster_kernel = d.por ? k_sat_cluster<true, 1024, 2, 64> : k_sat_cluster<false, 1024, 2, 64>;
+    if (half_tiles) {
+        cluster_kernel = d.por ? k_sat_cluster<true, 512, 2, 0> : k_sat_cluster<false, 512, 2, 0>;
+        if (d.Ny == 128) cluster_kernel = d.por ? k_sat_cluster<true, 512, 2, 128> : k_sat_cluster<false, 512, 2, 128>;
+        if (d.Ny == 64) cluster_kernel = d.por ? k_sat_cluster<true, 512, 2, 64> : k_sat_cluster<false, 512, 2, 64>;
+    }
     if (use_cluster) {
         HM_CUDA(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cluster));
         if (gc.nTiles > 8) HM_CUDA(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    }
+
+    // streaming transport (grids whose tiles do not fit a cluster, or sat_block 1): bulk-copy staged kernel when the
+    // row length is even (16-byte copies), sat_block 5 forces the plain-load kernel
+    const size_t smem_stream = ((size_t)(3 * g.R + 3) * d.Ny + 2) * sizeof(double);
+    const bool use_stream_tma = d.sat_block != 5 && d.Ny % 2 == 0 && smem_stream <= 75 * 1024;
+    if (use_stream_tma) {
+        HM_CUDA(cudaFuncSetAttribute(k_sat_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream));
+        HM_CUDA(cudaFuncSetAttribute(k_sat_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream));
     }
 
     // initial state: S <- S0, P <- 0 (cold start of the first solve), flags
@@ -685,7 +840,7 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
     HM_CUDA(cudaMemsetAsync(TXl + vec, 0, (size_t)d.Ny * sizeof(double), st));
     HM_CUDA(cudaMemsetAsync(TYl + vec, 0, sizeof(double), st));
     HM_CUDA(cudaMemsetAsync(Vxl + vec, 0, (size_t)d.Ny * sizeof(double), st));
-    HM_CUDA(cudaMemsetAsync(Vyl + vec, 0, sizeof(double), st));
+    HM_CUDA(cudaMemsetAsync(Vyl + vec, 0, 2 * sizeof(double), st));
     HM_CUDA(cudaMemsetAsync(cg_fail, 0, nm * sizeof(int), st));
     if (S_hist) k_copy_rows<<<copy_blocks, 256, 0, st>>>(nm, (int)M, Sa, M, S_hist, (int64_t)(d.n_steps + 1) * M);
     ctx->sim_stats.kernel_launches += 1 + (S_hist ? 1 : 0);
@@ -739,13 +894,26 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
             cfg.attrs = attr;
             cfg.numAttrs = 1;
             const double* porp = d.por;
+            if (step == 0 && getenv("HM_DEBUG")) {
+                int nc = -1;
+                cudaOccupancyMaxActiveClusters(&nc, cluster_kernel, &cfg);
+                fprintf(stderr, "[hm] k_sat_cluster: cluster of %d CTAs x %d threads, %zu B smem: max active clusters %d "
+                        "(%d CTAs on %d SMs)\n", gc.nTiles, cluster_threads, smem_cluster, nc, nc * gc.nTiles, ctx->sm_count);
+            }
             HM_CUDA(cudaLaunchKernelEx(&cfg, cluster_kernel, gc, fl, w, step, d.dt, (const int*)nts, (const double*)Scur,
                                        Snxt, (const double*)Vxl, (const double*)Vyl, porp));
             std::swap(Scur, Snxt);
             sat_launches = 1;
         } else {
             for (int it = 0; it < max_nts; ++it, ++sat_launches) {
-                if (d.por)
+                if (use_stream_tma) {
+                    if (d.por)
+                        k_sat_stream<true><<<grid, kStreamThreads, smem_stream, st>>>(g, fl, w, step, it, d.dt, nts, Scur,
+                                                                                     Snxt, Vxl, Vyl, d.por);
+                    else
+                        k_sat_stream<false><<<grid, kStreamThreads, smem_stream, st>>>(g, fl, w, step, it, d.dt, nts, Scur,
+                                                                                      Snxt, Vxl, Vyl, nullptr);
+                } else if (d.por)
                     k_sat_substep<true><<<grid, kThreads, smem1, st>>>(g, fl, w, step, it, d.dt, nts, Scur, Snxt,
                                                                         Vxl, Vyl, d.por);
                 else
@@ -795,8 +963,9 @@ int validate(const hm_sim_desc& d) {
     HM_REQUIRE(d.n_steps >= 0 && d.dt > 0, "dt, n_steps");
     HM_REQUIRE(d.n_obs == 0 || d.obs_cell, "obs_cell");
     HM_REQUIRE(d.Ny <= 1024, "Ny <= 1024 (row tiles of at least two grid rows must fit 2048 cells)");
-    HM_REQUIRE(d.precond >= 0 && d.precond <= 3,
-               "precond: 0 = multigrid V-cycle, 1 = Jacobi, 2 = multigrid W-cycle, 3 = multigrid V-cycle in FP32");
+    HM_REQUIRE(d.precond >= 0 && d.precond <= 4,
+               "precond: 0 = multigrid V-cycle (FP32 cycle, FP64 fallback), 1 = Jacobi, 2 = FP64 W-cycle, 3 = FP32 V-cycle, "
+               "4 = FP64 V-cycle");
     return HM_OK;
 }
 
@@ -807,6 +976,7 @@ extern "C" int hm_sim_batch(hm_ctx* ctx, const hm_sim_desc* desc) {
     HM_CHECK(validate(*desc));
     HM_CUDA(cudaSetDevice(ctx->device));
     ctx->sim_stats = hm_sim_stats{};
+    ctx->mg_force64 = false;
     for (double& v : ctx->phase_ms) v = 0.0;
     const int chunk = desc->chunk_members > 0 ? std::min(desc->chunk_members, desc->n_members)
                                               : desc->n_members;

@@ -32,13 +32,26 @@ def center(E, axis=0, rescale=False):
     return X, mu.squeeze()
 
 
+def _on_device(x):
+    return type(x).__module__.startswith("torch")
+
+
 def cov(a, b):
-    """Cross-covariance of two samples with equal ensemble size (``tools/utils.py:31-39``)."""
+    """Cross-covariance of two samples with equal ensemble size (``tools/utils.py:31-39``).
+    Torch (CUDA) inputs are reduced on the device (``hm_corr``), numpy inputs on the host as in the reference."""
+    if _on_device(a):
+        from historymatching_b200 import analysis
+
+        return analysis.cov(a, b)
     return center(a)[0].T @ center(b)[0] / (len(b) - 1)
 
 
 def corr(a, b):
     """Cross-correlation built on ``cov``, clipped to +-999 (``tools/utils.py:42-55``)."""
+    if _on_device(a):
+        from historymatching_b200 import analysis
+
+        return analysis.corr(a, b)
     C = cov(a, b)
     sa = np.std(a.T, axis=-1, ddof=1)
     sb = np.std(b, axis=0, ddof=1, keepdims=True)

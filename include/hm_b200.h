@@ -100,13 +100,19 @@ typedef struct hm_sim_desc {
     double cg_rtol;      /* <=0: default 1e-12 (||r|| <= rtol ||q||) */
     int32_t cg_max_iter; /* <=0: default 100*(Nx+Ny)+200 */
     int32_t chunk_members; /* <=0: all members in one launch wave */
-    int32_t precond;       /* pressure preconditioner: 0 = multigrid V-cycle (default), 1 = Jacobi, 2 = multigrid W-cycle,
-                            * 3 = multigrid V-cycle in FP32 arithmetic (CG itself stays FP64) */
+    int32_t precond;       /* pressure preconditioner (CG itself, its operator and the convergence test are always FP64):
+                            * 0 = multigrid V-cycle, default: the cycle runs in FP32 arithmetic; a solve that needs more than
+                            *     40 iterations restarts with the FP64 cycle and the rest of the call stays FP64
+                            *     (hm_sim_stats.mg_fp64_fallbacks); grids of <= 2048 cells: fused kernel, FP64 cycle;
+                            * 1 = Jacobi, 2 = FP64 multigrid W-cycle, 3 = FP32 V-cycle without fallback, 4 = FP64 V-cycle */
     int32_t sat_block;     /* kernel selection.  0 = automatic: grids of <= 2048 cells run the whole simulator in ONE kernel,
                             * one CTA per member (hm_small.cu); larger grids take the streamed path with the cluster
                             * transport kernel (all sub-steps of a time step in one launch) where a member's tiles fit a
                             * thread-block cluster, else the streaming transport kernel.  1 = streamed path, streaming
-                            * transport kernel (one sub-step per launch).  2 = streamed path, cluster transport kernel. */
+                            * transport kernel (one sub-step per launch).  2 = streamed path, cluster transport kernel.
+                            * The streaming kernel stages its tile with bulk copies (cp.async.bulk) when Ny is even.
+                            * 4 = as 2 with tiles of 1024 cells, 512 threads, two CTAs per SM (measured: same speed).
+                            * 5 = as 1 with the plain-load streaming kernel. */
     int32_t warm_start;    /* initial guess of a pressure solve: 0 = linear extrapolation of the two previous pressures
                             * (default), 1 = the previous pressure (measured: same iteration counts) */
 } hm_sim_desc;
@@ -118,6 +124,7 @@ typedef struct hm_sim_stats {
     int64_t kernel_launches; /* kernels launched by the call */
     int64_t cg_kernel_launches;
     int64_t sat_kernel_launches;
+    int64_t mg_fp64_fallbacks; /* pressure solves that switched from the FP32 to the FP64 multigrid cycle */
 } hm_sim_stats;
 
 /* All pointers in the descriptor are DEVICE pointers.  Synchronises the ctx
@@ -190,6 +197,14 @@ int hm_iles_step(hm_ctx* ctx, int64_t N, int64_t M, int64_t p, double* Ws, const
 /* E[:, i] = x0[i] + Ws[i] X0[:, i]  (recompose, HistoryMatch.py:1020-1021); E, X0 are (N,M). */
 int hm_iles_recompose(hm_ctx* ctx, int64_t N, int64_t M, const double* Ws, const double* X0,
                       const double* x0, double* E);
+
+/* Ensemble covariance / correlation fields.  Replaces utils.cov / utils.corr (tools/utils.py:31-55) as used
+ * by the correlation dashboards and the max-correlation paths (HistoryMatch.py:478-482, 738-748, 829-833)
+ * without pulling the ensemble to the host: a (N,M), b (N,q), out (M,q) row-major,
+ *   out = center(a)^T center(b) / (N-1)                                   (corr == 0)
+ *   out = clip(cov / std(a, ddof=1)[:,None] / std(b, ddof=1)[None,:], -999, 999)   (corr != 0). */
+int hm_corr(hm_ctx* ctx, int64_t N, int64_t M, int64_t q, const double* a, int64_t lda,
+            const double* b, int64_t ldb, double* out, int corr);
 
 #ifdef __cplusplus
 }

@@ -201,3 +201,47 @@ def test_iles_notebook_self_check_and_size(golden):
     E_gpu, _ = ha.ILES(obs_ens=fwd, taper=taper, xStep=0.4, iMax=2, **kw)
     E_ref, _ = oa.ILES(obs_ens=fwd, taper=taper, xStep=0.4, iMax=2, **kw)
     np.testing.assert_allclose(E_gpu, E_ref, **TOL)
+
+
+@pytest.mark.parametrize("N,M,q", [(40, 400, 1), (200, 400, 1), (64, 1000, 5), (33, 257, 19), (2, 7, 1)])
+def test_cov_corr_fields_vs_oracle(N, M, q):
+    """hm_corr against the oracle's utils.cov / utils.corr (tools/utils.py:31-55); b 1-D as in the notebook
+    (HistoryMatch.py:741, 831) and 2-D (cov for every q; corr for q > 1 with the (M,q) broadcasting)."""
+    import torch
+
+    from historymatching_b200 import analysis as ha
+    from historymatching_b200.dropin.tools import utils as dutils
+
+    rng = np.random.RandomState(N + M + q)
+    a = rng.randn(N, M) * (1 + 10 * rng.rand(M)) + 5 * rng.randn(M)
+    b = a[:, : max(q, 1)] @ rng.randn(max(q, 1), q) + rng.randn(N, q)
+    if q == 1:
+        b1 = b[:, 0]
+        np.testing.assert_allclose(ha.cov(a, b1), oa.cov(a, b1), rtol=1e-11, atol=1e-12)
+        got = ha.corr(a, b1)
+        assert got.shape == (M,)
+        np.testing.assert_allclose(got, oa.corr(a, b1), rtol=1e-11, atol=1e-13)
+        # device-resident inputs through the drop-in tools.utils
+        got_t = dutils.corr(torch.as_tensor(a, device="cuda"), torch.as_tensor(b1, device="cuda"))
+        assert got_t.is_cuda
+        np.testing.assert_array_equal(got_t.cpu().numpy(), got)
+        assert int(got_t.argmax()) == int(np.argmax(oa.corr(a, b1)))  # xy_max_corr, HistoryMatch.py:832
+    else:
+        np.testing.assert_allclose(ha.cov(a, b), oa.cov(a, b), rtol=1e-11, atol=1e-12)
+        ref = (oa.cov(a, b) / np.std(a, axis=0, ddof=1)[:, None] / np.std(b, axis=0, ddof=1)[None, :]).clip(-999, 999)
+        np.testing.assert_allclose(ha.corr(a, b), ref, rtol=1e-11, atol=1e-13)
+
+
+def test_corr_ill_defined_column():
+    """A constant column of a has zero spread: 0/0 -> NaN as in numpy (np.clip keeps NaN)."""
+    from historymatching_b200 import analysis as ha
+
+    rng = np.random.RandomState(0)
+    a = rng.randn(10, 6)
+    a[:, 2] = 1.5
+    b = rng.randn(10)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ref = oa.corr(a, b)
+    got = ha.corr(a, b)
+    assert np.isnan(got[2]) and np.isnan(ref[2])
+    np.testing.assert_allclose(np.delete(got, 2), np.delete(ref, 2), rtol=1e-11)

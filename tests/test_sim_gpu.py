@@ -50,10 +50,13 @@ def _oracle(m, logk, dt, nT, S0, prd):
 
 # sat_block 0 = automatic: grids of <= 2048 cells run in the fused one-CTA-per-member kernel (hm_small.cu),
 # larger ones on the streamed path; 2 = streamed path with the cluster transport kernel; 1 = streamed path
-# with the streaming transport kernel.
+# with the streaming transport kernel (bulk-copy staged when the row length is even); 5 = streamed path with the
+# plain-load streaming transport kernel.
 @pytest.mark.parametrize("Nx,Ny,N,nT,sat_block", [
     (20, 20, 6, 40, 0), (20, 20, 6, 40, 2), (33, 17, 3, 5, 0), (33, 17, 3, 5, 2), (33, 17, 3, 5, 1),
-    (45, 45, 2, 3, 0), (26, 30, 2, 4, 0), (64, 64, 2, 3, 0)])
+    (45, 45, 2, 3, 0), (26, 30, 2, 4, 0), (64, 64, 2, 3, 0),
+    # streaming transport: 1 = bulk-copy staged kernel (even row length), 5 = plain-load kernel
+    (26, 30, 2, 4, 1), (64, 64, 2, 3, 1), (26, 30, 2, 4, 5), (70, 36, 2, 2, 1)])
 def test_forward_ensemble_matches_oracle(Nx, Ny, N, nT, sat_block):
     from historymatching_b200.sim import run_ensemble
 
@@ -201,7 +204,7 @@ def test_extreme_contrast_floor(golden):
             assert err <= tol, (i, refine, err, tol)
 
 
-@pytest.mark.parametrize("sat_block", [0, 1, 2])
+@pytest.mark.parametrize("sat_block", [0, 1, 2, 5])
 def test_non_default_fluid_and_porosity(sat_block):
     """Viscosity ratio, irreducible saturations and a porosity field (both transport kernels)."""
     from historymatching_b200.sim import GridSpec, run_ensemble
@@ -224,3 +227,51 @@ def test_non_default_fluid_and_porosity(sat_block):
         ref, aux = om.sim(dt, nT, S0, return_aux=True)
         np.testing.assert_array_equal(res.substeps[i], aux["Nts"])
         np.testing.assert_allclose(res.S_hist[i], ref, rtol=0, atol=SAT_TOL)
+
+
+@pytest.mark.parametrize("precond", [0, 1, 2, 3, 4])
+def test_pressure_preconditioners_agree_with_oracle(precond):
+    """Every preconditioner (FP32 / FP64 V-cycle, W-cycle, Jacobi) solves to the same FP64 tolerance."""
+    from historymatching_b200.sim import run_ensemble
+
+    m, grid, logk, cells, rates, prd = _setup(64, 64, 2, seed=11)
+    dt, nT = 0.025, 3
+    res = run_ensemble(grid, orr.perm_transf(logk), cells, rates, np.zeros(grid.M), dt, nT, obs_cell=prd,
+                       history=True, pressure=True, want_substeps=True, precond=precond)
+    assert not res.status.any()
+    # precond 0 may switch to the FP64 cycle on this blocky field (it needs > 40 iterations); the others never do
+    assert res.stats["mg_fp64_fallbacks"] <= (nT if precond == 0 else 0)
+    wsats, _ = _oracle(m, logk, dt, nT, np.zeros(grid.M), prd)
+    np.testing.assert_allclose(res.S_hist, wsats, rtol=0, atol=SAT_TOL)
+
+
+def test_fp32_cycle_falls_back_to_fp64(monkeypatch):
+    """precond 0: a solve that is still running after HM_MG_SWITCH_ITERS iterations restarts CG with the FP64
+    cycle (here forced after 2 iterations); the result is unchanged and the rest of the run stays FP64."""
+    from historymatching_b200.sim import run_ensemble
+
+    m, grid, logk, cells, rates, prd = _setup(64, 48, 3, seed=5)
+    dt, nT = 0.025, 3
+    monkeypatch.setenv("HM_MG_SWITCH_ITERS", "2")
+    res = run_ensemble(grid, orr.perm_transf(logk), cells, rates, np.zeros(grid.M), dt, nT, obs_cell=prd,
+                       history=True, want_substeps=True)
+    assert not res.status.any()
+    assert res.stats["mg_fp64_fallbacks"] == 1  # sticky: only the first solve switches
+    wsats, _ = _oracle(m, logk, dt, nT, np.zeros(grid.M), prd)
+    np.testing.assert_allclose(res.S_hist, wsats, rtol=0, atol=SAT_TOL)
+
+
+@pytest.mark.parametrize("Nx,Ny", [(64, 64), (128, 128), (48, 64)])
+def test_half_tile_cluster_kernel_matches_default(Nx, Ny):
+    """sat_block 4 (1024-cell tiles, two CTAs per SM) against the default cluster kernel: same sub-step counts,
+    saturations equal to rounding (the two kernels evaluate the same expressions)."""
+    from historymatching_b200.sim import run_ensemble
+
+    m, grid, logk, cells, rates, prd = _setup(Nx, Ny, 3, seed=Nx)
+    dt, nT = 0.025, 2
+    kw = dict(obs_cell=prd, want_substeps=True)
+    a = run_ensemble(grid, orr.perm_transf(logk), cells, rates, np.zeros(grid.M), dt, nT, sat_block=2, **kw)
+    b = run_ensemble(grid, orr.perm_transf(logk), cells, rates, np.zeros(grid.M), dt, nT, sat_block=4, **kw)
+    assert not a.status.any() and not b.status.any()
+    np.testing.assert_array_equal(a.substeps, b.substeps)
+    np.testing.assert_allclose(b.S_last, a.S_last, rtol=0, atol=1e-12)
