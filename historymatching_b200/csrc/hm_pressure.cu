@@ -107,13 +107,13 @@ __device__ __forceinline__ void stv(U* p, const U (&v)[N]) {
 // are stored as vectors: the streamed multigrid kernels were bound by the LSU instruction rate (ncu: 58-66 % LSU
 // pipe, 34-37 % DRAM), not by HBM.  The global loads of a group pair are issued before its shared-memory phase.
 // NC == 0: runtime row length, one cell per lane and step.
-// OPS (FP32, row length 128): the operator rows are staged in shared memory as well (txs / tys, same row layout
-// as ds / bs), so the NU + 1 stencil passes of a tile touch global memory once instead of once per pass.
-template <typename T, typename TB, int NC, bool STAGE, bool OPS, typename F>
+// (Measured and dropped: staging the operator rows in shared memory as well - 6 arrays per tile, 3 CTAs per SM
+// instead of 5 - makes the pressure phase 9 % slower at 128^2 x 1024: occupancy matters more than the re-reads.)
+template <typename T, typename TB, int NC, bool STAGE, typename F>
 __device__ __forceinline__ void row_stencil(const T* xr, int ny, int lane, int c0, int li0,
                                             const T* __restrict__ TX, const T* __restrict__ TY,
                                             const T* __restrict__ dinv, const TB* __restrict__ b, const T* ds,
-                                            const T* bs, const T* txs, const T* tys, T pinv, F&& emit) {
+                                            const T* bs, T pinv, F&& emit) {
     if constexpr (NC != 0 && sizeof(T) == 4) {
         static_assert(NC % 4 == 0, "row length must be a multiple of 128");
         constexpr int NG = NC / 4;                                   // groups of 4 cells per lane
@@ -124,17 +124,10 @@ __device__ __forceinline__ void row_stencil(const T* xr, int ny, int lane, int c
 #pragma unroll
             for (int g = 0; g < GB; ++g) {
                 const int col = 128 * (g0 + g) + 4 * lane, c = c0 + col;
-                if constexpr (OPS) {
-                    ldv<4>(txs + li0 + col, tx0[g]);
-                    ldv<4>(txs + li0 + col + ny, tx1[g]);
-                    ldv<4>(tys + li0 + col, ty0[g]);
-                    tyr[g] = tys[li0 + col + 4];
-                } else {
-                    ldv<4>(TX + c, tx0[g]);
-                    ldv<4>(TX + c + ny, tx1[g]);
-                    ldv<4>(TY + c, ty0[g]);
-                    tyr[g] = TY[c + 4];
-                }
+                ldv<4>(TX + c, tx0[g]);
+                ldv<4>(TX + c + ny, tx1[g]);
+                ldv<4>(TY + c, ty0[g]);
+                tyr[g] = TY[c + 4];
                 if constexpr (STAGE) {
                     ldv<4>(ds + li0 + col, dv[g]);
                     ldv<4>(bs + li0 + col, bv[g]);
@@ -279,22 +272,6 @@ k_mg_down(Lvl<T> f, int cny, T* __restrict__ cb, const double* __restrict__ pin,
     T* xb = sm + L * ny;
     T* bs = sm + 2 * L * ny;
     T* ds = sm + 3 * L * ny;
-    constexpr bool OPS = STAGE && NY == 128;
-    T* txs = sm + 4 * L * ny;       // L + 1 rows: local row lr <-> low x-faces of grid row r0 - H + lr
-    T* tys = txs + (L + 1) * ny;    // L rows + 4 zeros
-    if constexpr (OPS) {
-        for (int lr = warp; lr < L + 1; lr += nW) {
-            const int row = r0 - H + lr;
-            const int col = 4 * lane;
-            T tx[4] = {0, 0, 0, 0}, ty[4] = {0, 0, 0, 0};
-            // row == nx reads the zero pad / the (zero) low faces of the next member's first row
-            if (row >= 0 && row <= f.nx) ldv<4>(TX + row * ny + col, tx);
-            if (row >= 0 && row < f.nx && lr < L) ldv<4>(TY + row * ny + col, ty);
-            stv<4>(txs + lr * ny + col, tx);
-            if (lr < L) stv<4>(tys + lr * ny + col, ty);
-            else if (lane == 0) stv<4>(tys + L * ny, ty);
-        }
-    }
     for (int lr = warp; lr < rows + 2 * H; lr += nW) {
         const int row = r0 - H + lr;
         const bool in = row >= 0 && row < f.nx;
@@ -345,7 +322,7 @@ k_mg_down(Lvl<T> f, int cny, T* __restrict__ cb, const double* __restrict__ pin,
             const int c0 = row * ny;
             const T* xr = xa + lr * ny;
             T* xo = xb + lr * ny;
-            row_stencil<T, TB, NY / 32, STAGE, OPS>(xr, ny, lane, c0, lr * ny, TX, TY, dinv, b, ds, bs, txs, tys, pinv,
+            row_stencil<T, TB, NY / 32, STAGE>(xr, ny, lane, c0, lr * ny, TX, TY, dinv, b, ds, bs, pinv,
                                                [&](auto n, int col, int, const auto& xc, const auto& dv, const auto& bv,
                                                    const auto& y) {
                                                    constexpr int NV = decltype(n)::value;
@@ -366,7 +343,7 @@ k_mg_down(Lvl<T> f, int cny, T* __restrict__ cb, const double* __restrict__ pin,
         const T* xr = xa + (lr + H) * ny;
         T* xo = xb + lr * ny;
         T* xg = f.xa + off;
-        row_stencil<T, TB, NY / 32, STAGE, OPS>(xr, ny, lane, c0, (lr + H) * ny, TX, TY, dinv, b, ds, bs, txs, tys, pinv,
+        row_stencil<T, TB, NY / 32, STAGE>(xr, ny, lane, c0, (lr + H) * ny, TX, TY, dinv, b, ds, bs, pinv,
                                            [&](auto n, int col, int c, const auto& xc, const auto&, const auto& bv,
                                                const auto& y) {
                                                constexpr int NV = decltype(n)::value;
@@ -430,22 +407,6 @@ k_mg_up(Lvl<T> f, int cny, const T* __restrict__ cx, const double* __restrict__ 
     T* xb = sm + L * ny;
     T* bs = sm + 2 * L * ny;
     T* ds = sm + 3 * L * ny;
-    constexpr bool OPS = STAGE && NY == 128;
-    T* txs = sm + 4 * L * ny;       // L + 1 rows: local row lr <-> low x-faces of grid row r0 - H + lr
-    T* tys = txs + (L + 1) * ny;    // L rows + 4 zeros
-    if constexpr (OPS) {
-        for (int lr = warp; lr < L + 1; lr += nW) {
-            const int row = r0 - H + lr;
-            const int col = 4 * lane;
-            T tx[4] = {0, 0, 0, 0}, ty[4] = {0, 0, 0, 0};
-            // row == nx reads the zero pad / the (zero) low faces of the next member's first row
-            if (row >= 0 && row <= f.nx) ldv<4>(TX + row * ny + col, tx);
-            if (row >= 0 && row < f.nx && lr < L) ldv<4>(TY + row * ny + col, ty);
-            stv<4>(txs + lr * ny + col, tx);
-            if (lr < L) stv<4>(tys + lr * ny + col, ty);
-            else if (lane == 0) stv<4>(tys + L * ny, ty);
-        }
-    }
     for (int lr = warp; lr < rows + 2 * H; lr += nW) {
         const int row = r0 - H + lr;
         const bool in = row >= 0 && row < f.nx;
@@ -499,7 +460,7 @@ k_mg_up(Lvl<T> f, int cny, const T* __restrict__ cx, const double* __restrict__ 
             const int c0 = row * ny;
             const T* xr = xa + lr * ny;
             T* xo = xb + lr * ny;
-            row_stencil<T, TB, NY / 32, STAGE, OPS>(xr, ny, lane, c0, lr * ny, TX, TY, dinv, b, ds, bs, txs, tys, pinv,
+            row_stencil<T, TB, NY / 32, STAGE>(xr, ny, lane, c0, lr * ny, TX, TY, dinv, b, ds, bs, pinv,
                                                [&](auto n, int col, int, const auto& xc, const auto& dv, const auto& bv,
                                                    const auto& y) {
                                                    constexpr int NV = decltype(n)::value;
@@ -518,7 +479,7 @@ k_mg_up(Lvl<T> f, int cny, const T* __restrict__ cx, const double* __restrict__ 
     for (int lr = warp; lr < rows; lr += nW) {
         const int c0 = (r0 + lr) * ny;
         const T* xr = xa + (lr + H) * ny;
-        row_stencil<T, TB, NY / 32, STAGE, OPS>(xr, ny, lane, c0, (lr + H) * ny, TX, TY, dinv, b, ds, bs, txs, tys, pinv,
+        row_stencil<T, TB, NY / 32, STAGE>(xr, ny, lane, c0, (lr + H) * ny, TX, TY, dinv, b, ds, bs, pinv,
                                            [&](auto n, int, int c, const auto& xc, const auto& dv, const auto& bv,
                                                const auto& y) {
                                                constexpr int NV = decltype(n)::value;
@@ -804,11 +765,7 @@ struct MgHierarchy {
     size_t nPart = 0;
     double* Ainv = nullptr;  // [member][n][n]: dense inverse (FP64) of the coarsest level
 
-    size_t smem_level(int l) const {
-        const size_t L = (size_t)lv[l].R + 2 * kNu, ny = (size_t)lv[l].ny;
-        if (sizeof(T) == 4 && l == 0 && ny == 128) return (6 * L * ny + ny + 4) * sizeof(T);  // + staged operator rows
-        return (size_t)(sizeof(T) == 4 ? 4 : 2) * L * ny * sizeof(T);
-    }
+    size_t smem_level(int l) const { return (size_t)(sizeof(T) == 4 ? 4 : 2) * (lv[l].R + 2 * kNu) * lv[l].ny * sizeof(T); }
 
     int build(hm_ctx* ctx, const Geo& g, int nm_, const double* TXl, const double* TYl, const double* dinv,
               const double* pin_, double* Rv, double* Z, bool wcycle, int* done_, double* part_rz_, size_t nPart_) {

@@ -409,6 +409,14 @@ k_sat_stream(Geo g, Fluid fl, Wells w, int step, int it, double dt, const int* _
     }
 }
 
+// predicated form: no branch (and no convergence barrier) around the store in the sub-step loop
+__device__ __forceinline__ void st_async_f64_if(bool pred, uint32_t remote_addr, double v, uint32_t remote_bar) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\t"
+        "@p st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];\n\t}" ::"r"(remote_addr),
+        "l"(__double_as_longlong(v)), "r"(remote_bar), "r"((int)pred) : "memory");
+}
+
 template <bool HAS_POR, int NT, int CPT, int NY>
 __global__ void __launch_bounds__(NT, NT <= 512 ? 2 : 1)
 k_sat_cluster(Geo g, Fluid fl, Wells w, int step, double dt, const int* __restrict__ nts,
@@ -486,6 +494,10 @@ k_sat_cluster(Geo g, Fluid fl, Wells w, int step, double dt, const int* __restri
         mbar_init(bar0, 1);
         mbar_init(bar1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (fast && nNbr) {  // fast path: first expectation of either barrier, re-posted by the waiters in the loop
+            mbar_expect_tx(bar0, nNbr * Ny * 8);
+            mbar_expect_tx(bar1, nNbr * Ny * 8);
+        }
     }
     // shared::cluster addresses of the neighbours' halo rows and barriers, per buffer parity
     uint32_t up0 = 0, up1 = 0, dn0 = 0, dn1 = 0, upb0 = 0, upb1 = 0, dnb0 = 0, dnb1 = 0;
@@ -525,34 +537,37 @@ k_sat_cluster(Geo g, Fluid fl, Wells w, int step, double dt, const int* __restri
         const bool needWait = sUp || sDn;
         const uint32_t colb = 8u * (uint32_t)col;
         const bool unit = fl.inv_range == 1.0 && fl.swc_ir == 0.0 && fl.mr == 1.0;
-        const bool lead = threadIdx.x < 32;  // warp-uniform: only warp 0 runs the expect_tx branch
-        bool anySrc = false;
-#pragma unroll
-        for (int j = 0; j < CPT; ++j) anySrc = anySrc || sr[j] != 0.0;
-        const bool warpSrc = __any_sync(0xffffffffu, anySrc);
+        // Transaction accounting of the halo mbarriers: every phase expects nNbr * Ny * 8 bytes.  The expectation of
+        // a barrier's NEXT phase is posted by one of the threads that has just seen the current phase complete (the
+        // edge row groups are the only waiters), so the 24 interior warps carry no barrier bookkeeping in the loop.
+        // (A neighbour's bytes may arrive before the expectation is posted: the transaction count goes negative
+        // for a moment, the phase cannot complete before the poster's arrival.)
+        const bool poster = needWait && (int)threadIdx.x == (hasUp ? 0 : NT - Ny);
+        const int haloBytes = nNbr * Ny * 8;
         auto substep = [&](auto unit_tag, double* __restrict__ fw, uint32_t mybar, uint32_t upA, uint32_t upB,
                            uint32_t dnA, uint32_t dnB, int parity) {
             constexpr bool U = decltype(unit_tag)::value;
-            if (lead) {
-                if (threadIdx.x == 0 && nNbr) mbar_expect_tx(mybar, nNbr * Ny * 8);
-            }
-            double f[CPT];
+            double f[CPT], ss[CPT];
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
                 f[j] = frac_flow_loop<U>(s[j], fl);
                 fw[j * Ny] = f[j];
+                ss[j] = s[j] + sr[j];  // injector source: beside the fw chain, not behind the update chain
             }
-            if (sUp) st_async_f64(upA + colb, f[0], upB);
-            if (sDn) st_async_f64(dnA + colb, f[CPT - 1], dnB);
+            st_async_f64_if(sUp, upA + colb, f[0], upB);
+            st_async_f64_if(sDn, dnA + colb, f[CPT - 1], dnB);
             double acc[CPT];  // the terms that only need this thread's registers, before the barrier
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
-                acc[j] = fma(dg[j], f[j], s[j]);
+                acc[j] = fma(dg[j], f[j], ss[j]);
                 if (j > 0) acc[j] = fma(aW[j], f[j - 1], acc[j]);
                 if (j < CPT - 1) acc[j] = fma(aE[j], f[j + 1], acc[j]);
             }
             __syncthreads();
-            if (needWait) mbar_wait(mybar, parity);
+            if (needWait) {
+                mbar_wait(mybar, parity);
+                if (poster) mbar_expect_tx(mybar, haloBytes);
+            }
             double fS[CPT], fN[CPT];
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
@@ -567,13 +582,6 @@ k_sat_cluster(Geo g, Fluid fl, Wells w, int step, double dt, const int* __restri
                 if (j == 0) a2 = fma(aW[j], fWest, a2);
                 if (j == CPT - 1) a2 = fma(aE[j], fEast, a2);
                 s[j] = a2;
-            }
-            if (warpSrc) {  // warp-uniform branch (kept a branch by the opaque asm): only warps holding an injector cell
-#pragma unroll
-                for (int j = 0; j < CPT; ++j) {
-                    asm volatile("" : "+d"(s[j]));
-                    s[j] += sr[j];
-                }
             }
         };
         double* const fwa = fwb0 + Ny + e0;

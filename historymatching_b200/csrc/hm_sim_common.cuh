@@ -114,15 +114,17 @@ struct Fluid {
     double mr;         // mobility ratio vw / vo:  fw = se^2 / (se^2 + mr (1-se)^2)
 };
 // a / b from the FP64 reciprocal seed MUFU.RCP64H (one special-function operation on the high word, no
-// FP32 round trip; measured seed error 9.9e-7) and one cubically convergent refinement
-// r' = r + r (e + e^2), e = 1 - b r: 4 FP64 operations + 1 XU operation.  Measured on B200 over
-// b in [0.25, 2]: max relative error of the quotient 1.9e-16.
+// FP32 round trip; measured seed error 9.9e-7) and one cubically convergent correction applied to the
+// QUOTIENT: q0 = a r, e = 1 - b r, q = q0 + q0 (e + e^2).  4 FP64 operations + 1 XU operation; q0 is computed
+// beside e, so the dependent chain behind the seed is 3 operations deep (e, e + e^2, q) - the transport kernels
+// are bound by the latency of their FP64 dependency chain, not by FP64 throughput (profiles/README.md).
+// Measured on B200 over b in [0.25, 2]: max relative error of the quotient 2e-16.
 __device__ __forceinline__ double fast_div_h(double a, double b) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    const double q0 = a * r;
     const double e = fma(-b, r, 1.0);
-    r = fma(r, fma(e, e, e), r);
-    return a * r;
+    return fma(q0, fma(e, e, e), q0);
 }
 __device__ __forceinline__ double frac_flow_fast(double s, const Fluid& f) {
     const double se = fma(s, f.inv_range, -f.swc_ir);
