@@ -376,7 +376,10 @@ def main():
     pcg_name = "MG-PCG iteration (k_mg_down+k_mg_onchip+k_mg_up+k_cg_spmv+k_cg_update)"
     cluster = stats_acc["sat_kernel_launches"] <= args.steps * wl["nTime"]  # one launch per time step
     sat_name = "k_sat_cluster (all CFL sub-steps of a time step, register/DSMEM resident)" if cluster else "k_sat_substep"
-    cg_bytes = 206.0 * M * cg_member_iters
+    # FP64 cycle: k_mg_down 50 + k_mg_up 60 + k_cg_spmv 48 + k_cg_update 48 = 206 B; FP32 cycle (the default): the cycle's
+    # operators and iterates are 4-byte, k_mg_down 25 (r 8, 1/diag 4, TX TY 8, x 4, coarse rhs 1) + k_mg_up 33 = 154 B
+    pcg_bytes_per_cell = 154.0 if (args.precond in (0, 3) and stats_acc["mg_fp64_fallbacks"] == 0) else 206.0
+    cg_bytes = pcg_bytes_per_cell * M * cg_member_iters
     sat_bytes = 32.0 * M * sat_member_substeps
     cands = {
         pcg_name: (cg_bytes, phase["cg"], stats_acc["cg_kernel_launches"] / 6),
@@ -403,10 +406,23 @@ def main():
         sm_hz = (sampler.summary()["sm_mhz"] or 1965.0) * 1e6
         roofline["on_chip_reuse_factor"] = 32.0 * nts_mean / 40.0
         roofline["hbm_bytes_per_launch_actual"] = 40.0 * M * N_loc
-        roofline["fp64_pipe_frac"] = 13.0 * M * sat_member_substeps / (t_ms * 1e-3) / (148 * 64 * sm_hz)
-        roofline["note"] = ("streaming model of SURVEY 8(d); the kernel keeps S and the upwind coefficients in "
-                            "registers for all sub-steps of a time step, so it is FP64-pipe / latency bound, not "
-                            "HBM bound: frac > 1 is the on-chip reuse factor at work")
+        # The binding resources, against peaks MEASURED on this GPU (profiles/tools/probe_fp64.cu, profiles/probe_r1.txt):
+        # FP64 pipe 61.5 lanes/clk/SM (DFMA: 2.08 cycles per warp instruction and SM sub-partition); the shared-memory
+        # crossbar 128 B/clk/SM (LDS.64: 2.04 cycles per warp instruction).  Per cell and sub-step the kernel issues 13
+        # FP64 instructions and moves 32 B through shared memory (1 store + 3 loads of fw).
+        sm_n = 148
+        resident = int(last["res"].stats.get("sat_resident_ctas", 0))
+        roofline["fp64_pipe_frac"] = 13.0 * M * sat_member_substeps / (t_ms * 1e-3) / (sm_n * 61.5 * sm_hz)
+        smem_peak = sm_n * 128.0 * sm_hz / 1e9
+        smem_ach = 32.0 * M * sat_member_substeps / (t_ms * 1e-3) / 1e9
+        roofline["smem_crossbar"] = dict(achieved=smem_ach, peak=smem_peak, unit="GB/s", frac=smem_ach / smem_peak)
+        roofline["resident_ctas"] = resident
+        roofline["sm_coverage"] = min(1.0, resident / sm_n) if resident else None
+        roofline["note"] = ("streaming model of SURVEY 8(d) (32 B per cell and sub-step); the kernel keeps S and the upwind "
+                            "coefficients in registers for all sub-steps of a time step and touches HBM once per time step, "
+                            "so frac > 1 is the on-chip reuse factor at work.  What binds it is on-chip: the shared-memory "
+                            "crossbar (fw exchange, smem_crossbar.frac) and the FP64 pipe (fp64_pipe_frac), which alternate "
+                            "around the one CTA barrier per sub-step, on the SMs the 8-CTA clusters can occupy (sm_coverage)")
         prof = os.path.join(ROOT, "profiles", "ncu_k_sat_cluster.json")
         if os.path.exists(prof) and (wl["Nx"], wl["Ny"], N_loc) == (128, 128, 1024):
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch at exactly this configuration

@@ -71,33 +71,6 @@ __device__ __forceinline__ T stencil(const T* xr, int col, int ny, const T* __re
     return y;
 }
 
-// Vector access helpers: N consecutive elements at a 16-byte aligned address as 128-bit transactions.
-template <int N, typename U>
-__device__ __forceinline__ void ldv(const U* p, U (&v)[N]) {
-    if constexpr (N == 4 && sizeof(U) == 4) {
-        const float4 t = *reinterpret_cast<const float4*>(p);
-        v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
-    } else if constexpr (N == 4 && sizeof(U) == 8) {
-        const double2 t0 = *reinterpret_cast<const double2*>(p), t1 = *reinterpret_cast<const double2*>(p + 2);
-        v[0] = t0.x, v[1] = t0.y, v[2] = t1.x, v[3] = t1.y;
-    } else {
-#pragma unroll
-        for (int k = 0; k < N; ++k) v[k] = p[k];
-    }
-}
-template <int N, typename U>
-__device__ __forceinline__ void stv(U* p, const U (&v)[N]) {
-    if constexpr (N == 4 && sizeof(U) == 4) {
-        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    } else if constexpr (N == 4 && sizeof(U) == 8) {
-        *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
-        *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
-    } else {
-#pragma unroll
-        for (int k = 0; k < N; ++k) p[k] = v[k];
-    }
-}
-
 // One stencil evaluation per cell of a whole grid row by a warp.  `emit(n_tag, col, c, xc, dv, bv, y)` receives
 // n = n_tag.value consecutive cells starting at column col / cell c: their iterate, 1/diag, right-hand side and
 // (A x).  Same arithmetic as stencil().
@@ -566,6 +539,61 @@ k_mg_onchip(const __grid_constant__ OnchipMeta mt, const T* __restrict__ b_in, T
     for (int e = threadIdx.x; e < M0; e += NT) x_out[(int64_t)m * M0 + e] = s.X[e];
 }
 
+// Vectorised variant for power-of-two hierarchies (v_cycle, hm_mg_onchip.cuh): padded X / TX / TY arrays, dense B /
+// DV, dense inverse behind them.  Same launch shape as k_mg_onchip.
+template <typename T>
+__global__ void __launch_bounds__(OnchipCfg<T>::NT, OnchipCfg<T>::CTAS)
+k_mg_onchip_v(const __grid_constant__ OnchipMeta mt, const T* __restrict__ b_in, T* __restrict__ x_out,
+              const double* __restrict__ pin, const int* __restrict__ done, const double* __restrict__ Ainv_g,
+              int ainv_off) {
+    constexpr int NT = OnchipCfg<T>::NT;
+    T* sm = smem_as<T>();
+    double* Ainv = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sm) + ainv_off);
+    const int m = blockIdx.x;
+    if (done[m]) return;
+    OnchipSmem<T> s;
+    s.X = sm;
+    s.TX = sm + mt.ptotal;
+    s.TY = sm + 2 * mt.ptotal;
+    s.B = sm + 3 * mt.ptotal;
+    s.DV = s.B + mt.total;
+    const T zero[4] = {0, 0, 0, 0};
+    for (int e = 4 * threadIdx.x; e < 3 * mt.ptotal; e += 4 * NT) stv<4>(sm + e, zero);  // iterate and the zero pads
+    {
+        const int nn = mt.M[mt.n - 1] * mt.M[mt.n - 1];
+        for (int e = threadIdx.x; e < nn; e += NT) Ainv[e] = Ainv_g[(int64_t)m * nn + e];
+    }
+    __syncthreads();
+    for (int l = 0; l < mt.n; ++l) {
+        const int64_t g = (int64_t)m * mt.M[l];
+        const T* tx = static_cast<const T*>(mt.TX[l]) + g;
+        const T* ty = static_cast<const T*>(mt.TY[l]) + g;
+        const T* dv = static_cast<const T*>(mt.dinv[l]) + g;
+        for (int e = 4 * threadIdx.x; e < mt.M[l]; e += 4 * NT) {
+            T v[4];
+            ldv<4>(tx + e, v);
+            stv<4>(s.TX + mt.poff[l] + e, v);
+            ldv<4>(ty + e, v);
+            stv<4>(s.TY + mt.poff[l] + e, v);
+            ldv<4>(dv + e, v);
+            stv<4>(s.DV + mt.off[l] + e, v);
+        }
+    }
+    const int M0 = mt.M[0];
+    for (int e = 4 * threadIdx.x; e < M0; e += 4 * NT) {
+        T v[4];
+        ldv<4>(b_in + (int64_t)m * M0 + e, v);
+        stv<4>(s.B + e, v);
+    }
+    __syncthreads();
+    v_cycle<T, NT, kOnchipCells / 4 / NT>(mt, s, (T)pin[m], Ainv);
+    for (int e = 4 * threadIdx.x; e < M0; e += 4 * NT) {
+        T v[4];
+        ldv<4>(s.X + mt.poff[0] + e, v);
+        stv<4>(x_out + (int64_t)m * M0 + e, v);
+    }
+}
+
 // ---- CG kernels -------------------------------------------------------------------------------
 // r = q - A x0 (warm start), optional Jacobi z = r/diag; partial (r,z), (r,r); ||q||^2
 template <bool JACOBI>
@@ -759,6 +787,7 @@ struct MgHierarchy {
     OnchipMeta mt{};
     size_t smemOn = 0;
     int ainvOff = 0;
+    bool vecOn = false;  // the on-chip levels run the vectorised cycle (k_mg_onchip_v)
     const double* pin = nullptr;
     int* done = nullptr;
     double* part_rz = nullptr;
@@ -862,6 +891,40 @@ struct MgHierarchy {
         mt.wmin = wcycle ? kWcycleMinCells : 0x7fffffff;
         ainvOff = (int)((((size_t)5 * o * sizeof(T)) + 7) & ~(size_t)7);
         smemOn = (size_t)ainvOff + (size_t)lv[nLev - 1].M * lv[nLev - 1].M * sizeof(double);
+        // vectorised cycle (k_mg_onchip_v): V-cycle on a hierarchy whose levels above the coarsest have a power-of-two
+        // row length in [8, 64], an even number of rows and halve exactly; padded layout for X, TX, TY
+        vecOn = !wcycle && mt.n >= 2;
+        int po = 0;
+        for (int i = 0; i < mt.n; ++i) {
+            const int ny_i = mt.ny[i], nx_i = mt.nx[i];
+            if (i < mt.n - 1) {
+                const bool pow2 = ny_i == 8 || ny_i == 16 || ny_i == 32 || ny_i == 64;
+                vecOn = vecOn && pow2 && nx_i % 2 == 0 && mt.ny[i + 1] * 2 == ny_i && mt.nx[i + 1] * 2 == nx_i;
+                int lg = 0;
+                while ((4 << lg) < ny_i) ++lg;
+                mt.lgpr[i] = lg;
+            }
+            // zero pad in front of the level: its own row length + 4 for the reads below index 0, and the row length of
+            // the level above (stored in front of it), whose last row reads one row past its end
+            const int pad = std::max(ny_i, i > 0 ? mt.ny[i - 1] : 0) + 4;
+            po += (pad + 3) & ~3;
+            mt.poff[i] = po;
+            po += (mt.M[i] + 3) & ~3;
+        }
+        po += (mt.ny[mt.n - 1] + 4 + 3) & ~3;
+        mt.ptotal = po;
+        if (vecOn) {
+            const size_t aoff = ((size_t)(3 * mt.ptotal + 2 * mt.total) * sizeof(T) + 7) & ~(size_t)7;
+            const size_t sm_v = aoff + (size_t)lv[nLev - 1].M * lv[nLev - 1].M * sizeof(double);
+            const size_t limit = (size_t)(232448 - 1024 * OnchipCfg<T>::CTAS) / OnchipCfg<T>::CTAS;
+            if (sm_v <= limit) {
+                ainvOff = (int)aoff;
+                smemOn = sm_v;
+                HM_CUDA(cudaFuncSetAttribute(k_mg_onchip_v<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemOn));
+            } else {
+                vecOn = false;
+            }
+        }
         HM_CUDA(cudaFuncSetAttribute(k_mg_onchip<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemOn));
         {   // dense inverse of the coarsest level, one warp per member
             const Lvl<T>& L = lv[nLev - 1];
@@ -904,8 +967,12 @@ struct MgHierarchy {
             else
                 k_mg_down<T, false><<<grid, kThreads, sm, st>>>(lv[l], lv[l + 1].ny, cb, pin, done);
         }
-        k_mg_onchip<T><<<nm, OnchipCfg<T>::NT, smemOn, st>>>(mt, static_cast<const T*>(lv[firstOn].b),
-                                                              static_cast<T*>(lv[firstOn].xb), pin, done, Ainv, ainvOff);
+        if (vecOn)
+            k_mg_onchip_v<T><<<nm, OnchipCfg<T>::NT, smemOn, st>>>(mt, static_cast<const T*>(lv[firstOn].b),
+                                                                    static_cast<T*>(lv[firstOn].xb), pin, done, Ainv, ainvOff);
+        else
+            k_mg_onchip<T><<<nm, OnchipCfg<T>::NT, smemOn, st>>>(mt, static_cast<const T*>(lv[firstOn].b),
+                                                                  static_cast<T*>(lv[firstOn].xb), pin, done, Ainv, ainvOff);
         for (int l = firstOn - 1; l >= 0; --l) {
             const T* cx = static_cast<const T*>(lv[l + 1].xb);
             const int grid = nm * lv[l].nTiles;

@@ -902,11 +902,13 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
             cfg.attrs = attr;
             cfg.numAttrs = 1;
             const double* porp = d.por;
-            if (step == 0 && getenv("HM_DEBUG")) {
-                int nc = -1;
-                cudaOccupancyMaxActiveClusters(&nc, cluster_kernel, &cfg);
-                fprintf(stderr, "[hm] k_sat_cluster: cluster of %d CTAs x %d threads, %zu B smem: max active clusters %d "
-                        "(%d CTAs on %d SMs)\n", gc.nTiles, cluster_threads, smem_cluster, nc, nc * gc.nTiles, ctx->sm_count);
+            if (step == 0) {  // how many CTAs of this kernel the GPU holds at once (clusters must fit a GPC)
+                int nc = 0;
+                if (cudaOccupancyMaxActiveClusters(&nc, cluster_kernel, &cfg) == cudaSuccess)
+                    ctx->sim_stats.sat_resident_ctas = (int64_t)nc * gc.nTiles;
+                if (getenv("HM_DEBUG"))
+                    fprintf(stderr, "[hm] k_sat_cluster: cluster of %d CTAs x %d threads, %zu B smem: max active clusters %d "
+                            "(%d CTAs on %d SMs)\n", gc.nTiles, cluster_threads, smem_cluster, nc, nc * gc.nTiles, ctx->sm_count);
             }
             HM_CUDA(cudaLaunchKernelEx(&cfg, cluster_kernel, gc, fl, w, step, d.dt, (const int*)nts, (const double*)Scur,
                                        Snxt, (const double*)Vxl, (const double*)Vyl, porp));

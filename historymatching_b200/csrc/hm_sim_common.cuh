@@ -142,4 +142,31 @@ __device__ __forceinline__ double frac_flow_loop(double s, const Fluid& f) {
 }
 
 
+// Vector access helpers: N consecutive elements at a 16-byte aligned address as 128-bit transactions.
+template <int N, typename U>
+__device__ __forceinline__ void ldv(const U* p, U (&v)[N]) {
+    if constexpr (N == 4 && sizeof(U) == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+    } else if constexpr (N == 4 && sizeof(U) == 8) {
+        const double2 t0 = *reinterpret_cast<const double2*>(p), t1 = *reinterpret_cast<const double2*>(p + 2);
+        v[0] = t0.x, v[1] = t0.y, v[2] = t1.x, v[3] = t1.y;
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) v[k] = p[k];
+    }
+}
+template <int N, typename U>
+__device__ __forceinline__ void stv(U* p, const U (&v)[N]) {
+    if constexpr (N == 4 && sizeof(U) == 4) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    } else if constexpr (N == 4 && sizeof(U) == 8) {
+        *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) p[k] = v[k];
+    }
+}
+
 }  // namespace hmsim
