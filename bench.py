@@ -252,6 +252,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL writes its version / debug lines to stdout by default; stdout carries the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     from historymatching_b200 import _lib
     from historymatching_b200 import analysis as ha
@@ -278,6 +280,11 @@ def main():
     ctx = _lib.Context.get(local_rank)
 
     last = {}
+    t_start = time.perf_counter()
+
+    def log(msg):
+        if os.environ.get("HM_BENCH_LOG") and rank == 0:
+            print(f"[bench +{time.perf_counter() - t_start:7.1f}s] {msg}", file=sys.stderr, flush=True)
 
     def one_pass(E):
         Eo, res = case.forward(E, want_substeps=True, sat_block=args.sat_block, precond=args.precond)
@@ -295,8 +302,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    log("inputs ready")
     for _ in range(args.warmup):
         one_pass(E0)
+        torch.cuda.synchronize()
+        log("warm-up pass done")
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -320,6 +330,7 @@ def main():
             stats_acc[k] += res.stats[k]
     ev1.record()
     torch.cuda.nvtx.range_pop()
+    log("timed passes done")
     barrier()
     sampler.stop_flag.set()
     sampler.join()
@@ -375,7 +386,9 @@ def main():
     hbm = float(pk.get("hbm_gbs", PEAKS_FALLBACK["hbm_gbs"]))
     pcg_name = "MG-PCG iteration (k_mg_down+k_mg_onchip+k_mg_up+k_cg_spmv+k_cg_update)"
     cluster = stats_acc["sat_kernel_launches"] <= args.steps * wl["nTime"]  # one launch per time step
-    sat_name = "k_sat_cluster (all CFL sub-steps of a time step, register/DSMEM resident)" if cluster else "k_sat_substep"
+    stream_name = ("k_sat_stream (one sub-step per launch, tile staged by bulk copies)"
+                   if wl["Ny"] % 2 == 0 and args.sat_block != 5 else "k_sat_substep (one sub-step per launch, plain loads)")
+    sat_name = "k_sat_cluster (all CFL sub-steps of a time step, register/DSMEM resident)" if cluster else stream_name
     # FP64 cycle: k_mg_down 50 + k_mg_up 60 + k_cg_spmv 48 + k_cg_update 48 = 206 B; FP32 cycle (the default): the cycle's
     # operators and iterates are 4-byte, k_mg_down 25 (r 8, 1/diag 4, TX TY 8, x 4, coarse rhs 1) + k_mg_up 33 = 154 B
     pcg_bytes_per_cell = 154.0 if (args.precond in (0, 3) and stats_acc["mg_fp64_fallbacks"] == 0) else 206.0

@@ -782,7 +782,8 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
     w.rate = d.well_rate + (int64_t)m0 * d.well_rate_member_stride;
     w.rate_ms = d.well_rate_member_stride;
     w.rate_ss = d.well_rate_step_stride;
-    double* S_hist = d.S_hist ? d.S_hist + (int64_t)m0 * (d.n_steps + 1) * M : nullptr;
+    const int nHist = hist_rows(d.n_steps, d.hist_stride);
+    double* S_hist = d.S_hist ? d.S_hist + (int64_t)m0 * nHist * M : nullptr;
     double* obs = d.obs ? d.obs + (int64_t)m0 * d.n_steps * d.n_obs : nullptr;
     int32_t* substeps = d.substeps ? d.substeps + (int64_t)m0 * d.n_steps : nullptr;
     int32_t* cg_iters_out = d.cg_iters ? d.cg_iters + (int64_t)m0 * d.n_steps : nullptr;
@@ -850,7 +851,7 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
     HM_CUDA(cudaMemsetAsync(Vxl + vec, 0, (size_t)d.Ny * sizeof(double), st));
     HM_CUDA(cudaMemsetAsync(Vyl + vec, 0, 2 * sizeof(double), st));
     HM_CUDA(cudaMemsetAsync(cg_fail, 0, nm * sizeof(int), st));
-    if (S_hist) k_copy_rows<<<copy_blocks, 256, 0, st>>>(nm, (int)M, Sa, M, S_hist, (int64_t)(d.n_steps + 1) * M);
+    if (S_hist) k_copy_rows<<<copy_blocks, 256, 0, st>>>(nm, (int)M, Sa, M, S_hist, (int64_t)nHist * M);
     ctx->sim_stats.kernel_launches += 1 + (S_hist ? 1 : 0);
 
     PhaseTimer timer(st);
@@ -942,9 +943,9 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
                                                                        obs, d.n_steps, step);
             ctx->sim_stats.kernel_launches += 1;
         }
-        if (S_hist) {
-            k_copy_rows<<<copy_blocks, 256, 0, st>>>(nm, (int)M, Scur, M, S_hist + (int64_t)(step + 1) * M,
-                                                      (int64_t)(d.n_steps + 1) * M);
+        const int hrow = hist_row(step + 1, d.n_steps, d.hist_stride);
+        if (S_hist && hrow >= 0) {
+            k_copy_rows<<<copy_blocks, 256, 0, st>>>(nm, (int)M, Scur, M, S_hist + (int64_t)hrow * M, (int64_t)nHist * M);
             ctx->sim_stats.kernel_launches += 1;
         }
         if (!all_done) {
@@ -1059,7 +1060,7 @@ extern "C" int hm_sim_batch_host(hm_ctx* ctx, const hm_sim_desc* hd) {
     HM_CHECK(ctx->ws.get("h.S_last", (size_t)nm * M * sizeof(double), &p));
     d.S_last = (double*)p;
     if (hd->S_hist) {
-        HM_CHECK(ctx->ws.get("h.S_hist", (size_t)nm * (d.n_steps + 1) * M * sizeof(double), &p));
+        HM_CHECK(ctx->ws.get("h.S_hist", (size_t)nm * hist_rows(d.n_steps, d.hist_stride) * M * sizeof(double), &p));
         d.S_hist = (double*)p;
     }
     if (hd->obs) {
@@ -1088,7 +1089,8 @@ extern "C" int hm_sim_batch_host(hm_ctx* ctx, const hm_sim_desc* hd) {
         return HM_OK;
     };
     HM_CHECK(down(hd->S_last, d.S_last, (size_t)nm * M * sizeof(double)));
-    if (hd->S_hist) HM_CHECK(down(hd->S_hist, d.S_hist, (size_t)nm * (d.n_steps + 1) * M * sizeof(double)));
+    if (hd->S_hist)
+        HM_CHECK(down(hd->S_hist, d.S_hist, (size_t)nm * hist_rows(d.n_steps, d.hist_stride) * M * sizeof(double)));
     if (hd->obs) HM_CHECK(down(hd->obs, d.obs, (size_t)nm * d.n_steps * d.n_obs * sizeof(double)));
     if (hd->P_last) HM_CHECK(down(hd->P_last, d.P_last, (size_t)nm * M * sizeof(double)));
     if (hd->status) HM_CHECK(down(hd->status, d.status, (size_t)nm * sizeof(int32_t)));

@@ -19,6 +19,17 @@ struct Geo {
     double vw, vo, swc, sor;
 };
 
+// Saturation history layout (hm_sim_desc.hist_stride): row 0 = S0, then the states after steps k, 2k, ... and after
+// the last step.  hist_row(step_done) = the row of the state after `step_done` steps, or -1 if it is not stored.
+__host__ __device__ __forceinline__ int hist_rows(int n_steps, int stride) {
+    return stride <= 1 ? n_steps + 1 : 1 + (n_steps + stride - 1) / stride;
+}
+__host__ __device__ __forceinline__ int hist_row(int step_done, int n_steps, int stride) {
+    if (stride <= 1) return step_done;
+    if (step_done % stride == 0) return step_done / stride;
+    return step_done == n_steps ? hist_rows(n_steps, stride) - 1 : -1;
+}
+
 struct Wells {
     int n;
     const int32_t* cell;

@@ -50,6 +50,7 @@ struct SmallArgs {
     const int32_t* obs_cell;
     double* S_last;
     double* S_hist;
+    int hist_stride;
     double* obs;
     double* P_last;
     int32_t* status;
@@ -294,7 +295,8 @@ k_sim_small(const __grid_constant__ SmallArgs a) {
     const double pinv = Kx[0] + Ky[0];  // pin of the singular Neumann problem: A[0,0] += Kx[0] + Ky[0]
     for (int e = tid; e < M; e += NT) S[e] = a.S0[(int64_t)m * a.S0_ms + e];
     if (a.S_hist)
-        for (int e = tid; e < M; e += NT) a.S_hist[(int64_t)m * (a.n_steps + 1) * M + e] = a.S0[(int64_t)m * a.S0_ms + e];
+        for (int e = tid; e < M; e += NT)
+            a.S_hist[(int64_t)m * hist_rows(a.n_steps, a.hist_stride) * M + e] = a.S0[(int64_t)m * a.S0_ms + e];
     __syncthreads();
 
     int cg_fail = 0, tot_iters = 0, tot_sub = 0;
@@ -485,8 +487,10 @@ k_sim_small(const __grid_constant__ SmallArgs a) {
         if (a.obs)
             for (int j = tid; j < a.n_obs; j += NT)
                 a.obs[((int64_t)m * a.n_steps + step) * a.n_obs + j] = S[a.obs_cell[j]];
-        if (a.S_hist)
-            for (int e = tid; e < M; e += NT) a.S_hist[((int64_t)m * (a.n_steps + 1) + step + 1) * M + e] = S[e];
+        const int hrow = hist_row(step + 1, a.n_steps, a.hist_stride);
+        if (a.S_hist && hrow >= 0)
+            for (int e = tid; e < M; e += NT)
+                a.S_hist[((int64_t)m * hist_rows(a.n_steps, a.hist_stride) + hrow) * M + e] = S[e];
         __syncthreads();
     }
     int bad = 0;
@@ -588,7 +592,8 @@ int sim_small(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
     a.n_obs = d.obs ? d.n_obs : 0;
     a.obs_cell = d.obs_cell;
     a.S_last = d.S_last + (int64_t)m0 * M;
-    a.S_hist = d.S_hist ? d.S_hist + (int64_t)m0 * (d.n_steps + 1) * M : nullptr;
+    a.S_hist = d.S_hist ? d.S_hist + (int64_t)m0 * hist_rows(d.n_steps, d.hist_stride) * M : nullptr;
+    a.hist_stride = d.hist_stride;
     a.obs = d.obs ? d.obs + (int64_t)m0 * d.n_steps * d.n_obs : nullptr;
     a.P_last = d.P_last ? d.P_last + (int64_t)m0 * M : nullptr;
     a.status = d.status ? d.status + m0 : nullptr;

@@ -65,6 +65,8 @@ def run_ensemble(grid: GridSpec, K, well_cell, well_rate, S0, dt, n_steps, *, n_
     well_rate  signed rates (+inj, -prd): (nW,) constant & shared; (nT,nW) shared
                schedule; (N,1,nW) / (N,nT,nW) per member
     S0         (M,) shared or (N,M)
+    history    True: ``S_hist (N, n_steps+1, M)`` (row 0 = S0, the reference's ``ResSim.sim`` output);
+               an int k > 1: every k-th step and the last one, ``(N, 1 + ceil(n_steps/k), M)``
     """
     M = grid.M
     use_torch = _is_torch(K)
@@ -147,7 +149,9 @@ def run_ensemble(grid: GridSpec, K, well_cell, well_rate, S0, dt, n_steps, *, n_
 
     res = SimResult(S_last=empty((N, M)))
     res.obs = empty((N, n_steps, n_obs)) if n_obs else None
-    res.S_hist = empty((N, n_steps + 1, M)) if history else None
+    hist_stride = int(history) if (history is not True and history) else (1 if history else 0)
+    n_hist = n_steps + 1 if hist_stride <= 1 else 1 + -(-n_steps // hist_stride)
+    res.S_hist = empty((N, n_hist, M)) if history else None
     res.P_last = empty((N, M)) if pressure else None
     res.status = empty((N,), i32)
     res.substeps = empty((N, n_steps), i32) if want_substeps else None
@@ -169,6 +173,7 @@ def run_ensemble(grid: GridSpec, K, well_cell, well_rate, S0, dt, n_steps, *, n_
     d.cg_rtol, d.cg_max_iter, d.chunk_members = float(cg_rtol), int(cg_max_iter), int(chunk_members)
     d.precond = int(precond)
     d.sat_block = int(sat_block)
+    d.hist_stride = hist_stride
     d.warm_start = int(warm_start)
 
     if use_torch:

@@ -90,7 +90,8 @@ typedef struct hm_sim_desc {
     const int32_t* obs_cell;  /* [n_obs] cells whose saturation is observed */
 
     double* S_last;   /* out [member][M] saturation after the last step */
-    double* S_hist;   /* out NULL or [member][n_steps+1][M], row 0 = S0 */
+    double* S_hist;   /* out NULL or [member][n_hist][M], row 0 = S0; n_hist = n_steps+1, or with hist_stride = k > 1
+                       * 1 + ceil(n_steps / k): the states after steps k, 2k, ... and after the last step */
     double* obs;      /* out NULL or [member][n_steps][n_obs] */
     double* P_last;   /* out NULL or [member][M] pressure of the last step */
     int32_t* status;  /* out NULL or [member] HM_MEMBER_* bits */
@@ -113,6 +114,9 @@ typedef struct hm_sim_desc {
                             * The streaming kernel stages its tile with bulk copies (cp.async.bulk) when Ny is even.
                             * 4 = as 2 with tiles of 1024 cells, 512 threads, two CTAs per SM (measured: same speed).
                             * 5 = as 1 with the plain-load streaming kernel. */
+    int32_t hist_stride;   /* <= 1: S_hist holds every step (the reference's ResSim.sim output); k > 1: every k-th step and
+                            * the last one - the saturation history of a large ensemble for plotting / animation cells
+                            * (HistoryMatch.py:233, 1212-1214) without n_steps+1 fields per member */
     int32_t warm_start;    /* initial guess of a pressure solve: 0 = linear extrapolation of the two previous pressures
                             * (default), 1 = the previous pressure (measured: same iteration counts) */
 } hm_sim_desc;

@@ -275,3 +275,18 @@ def test_half_tile_cluster_kernel_matches_default(Nx, Ny):
     assert not a.status.any() and not b.status.any()
     np.testing.assert_array_equal(a.substeps, b.substeps)
     np.testing.assert_allclose(b.S_last, a.S_last, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("Nx,Ny,nT,stride", [(20, 20, 7, 3), (20, 20, 6, 3), (64, 64, 5, 2), (64, 64, 4, 5)])
+def test_strided_history(Nx, Ny, nT, stride):
+    """history=k keeps rows 0, k, 2k, ... and the last step of the full history (fused and streamed path)."""
+    from historymatching_b200.sim import run_ensemble
+
+    m, grid, logk, cells, rates, prd = _setup(Nx, Ny, 3, seed=2)
+    args = (grid, orr.perm_transf(logk), cells, rates, np.zeros(grid.M), 0.025, nT)
+    full = run_ensemble(*args, history=True)
+    part = run_ensemble(*args, history=stride)
+    rows = sorted(set(range(0, nT + 1, stride)) | {nT})
+    assert part.S_hist.shape == (3, len(rows), grid.M)
+    np.testing.assert_array_equal(part.S_hist, full.S_hist[:, rows])
+    np.testing.assert_array_equal(part.S_last, full.S_last)
