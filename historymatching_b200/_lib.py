@@ -40,7 +40,7 @@ class SimDesc(C.Structure):
         ("S_last", C.c_void_p), ("S_hist", C.c_void_p), ("obs", C.c_void_p), ("P_last", C.c_void_p),
         ("status", C.c_void_p), ("substeps", C.c_void_p), ("cg_iters", C.c_void_p),
         ("cg_rtol", C.c_double), ("cg_max_iter", C.c_int32),
-        ("chunk_members", C.c_int32), ("precond", C.c_int32), ("sat_block", C.c_int32), ("hist_stride", C.c_int32), ("warm_start", C.c_int32),
+        ("chunk_members", C.c_int32), ("precond", C.c_int32), ("mg_switch_iters", C.c_int32), ("sat_block", C.c_int32), ("hist_stride", C.c_int32), ("warm_start", C.c_int32),
     ]
 
 

@@ -22,7 +22,6 @@
 // CG itself is two more streamed kernels per iteration (k_cg_spmv 48 B/cell,
 // k_cg_update 48 B/cell).  Members converge independently: a per-member `done`
 // flag makes the CTAs of converged members exit at once.
-#include <cstdlib>
 #include <type_traits>
 
 #include "hm_mg_onchip.cuh"
@@ -997,8 +996,8 @@ struct MgHierarchy {
 // ---- host side -----------------------------------------------------------------------------------
 int pressure_solve(hm_ctx* ctx, const Geo& g, const Wells& w, int step, int nm, const double* TXl,
                    const double* TYl, const double* dinv, const double* pin, double* P, double rtol,
-                   int max_iter, int precond, int* done, int* iters, int* counters, int* cg_batch,
-                   int* iters_used, bool* all_done_out) {
+                   int max_iter, int precond, int mg_switch_iters, int* done, int* iters, int* counters,
+                   int* cg_batch, int* iters_used, bool* all_done_out) {
     cudaStream_t st = ctx->stream;
     const int64_t M = g.M;
     const size_t vec = (size_t)nm * M;
@@ -1037,8 +1036,7 @@ int pressure_solve(hm_ctx* ctx, const Geo& g, const Wells& w, int step, int nm, 
     // starts from P = 0) restarts CG (beta = 0) with the FP64 cycle; when that happens on a warm-started solve
     // the rest of the forward run stays FP64 (ctx->mg_force64).  precond 4 = FP64 V-cycle, 2 = FP64 W-cycle,
     // 3 = FP32 V-cycle without fallback.
-    int kSwitchIters = step == 0 ? 80 : 40;
-    if (const char* e = getenv("HM_MG_SWITCH_ITERS")) kSwitchIters = std::max(1, atoi(e));  // test hook
+    const int kSwitchIters = mg_switch_iters > 0 ? mg_switch_iters : (step == 0 ? 80 : 40);
     MgHierarchy<float> mgf;
     MgHierarchy<double> mgd;
     const bool adaptive = precond == 0;
@@ -1097,7 +1095,7 @@ int pressure_solve(hm_ctx* ctx, const Geo& g, const Wells& w, int step, int nm, 
             HM_CHECK(mgd.build(ctx, g, nm, TXl, TYl, dinv, pin, Rv, Z, false, done, part_rz, nPart));
             mg32 = false;
             restart = true;
-            if (step > 0 || getenv("HM_MG_SWITCH_ITERS")) ctx->mg_force64 = true;
+            if (step > 0 || mg_switch_iters > 0) ctx->mg_force64 = true;
             ctx->sim_stats.mg_fp64_fallbacks += 1;
         }
     }

@@ -31,8 +31,8 @@ using namespace hmsim;
 namespace hmsim {
 int pressure_solve(hm_ctx* ctx, const Geo& g, const Wells& w, int step, int nm, const double* TXl,
                    const double* TYl, const double* dinv, const double* pin, double* P, double rtol,
-                   int max_iter, int precond, int* done, int* iters, int* counters, int* cg_batch,
-                   int* iters_used, bool* all_done_out);
+                   int max_iter, int precond, int mg_switch_iters, int* done, int* iters, int* counters,
+                   int* cg_batch, int* iters_used, bool* all_done_out);
 int sim_small_supported(const hm_sim_desc& d);
 int sim_small(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm);
 }
@@ -872,8 +872,8 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
         }
         int k = 0;
         bool all_done = false;
-        HM_CHECK(pressure_solve(ctx, g, w, step, nm, TXl, TYl, dinv, pin, P, rtol, max_iter, d.precond, done, iters,
-                                counters, &cg_batch, &k, &all_done));
+        HM_CHECK(pressure_solve(ctx, g, w, step, nm, TXl, TYl, dinv, pin, P, rtol, max_iter, d.precond, d.mg_switch_iters,
+                                done, iters, counters, &cg_batch, &k, &all_done));
         ctx->sim_stats.kernel_launches += 1;
         if (cg_iters_out)
             k_record_iters<<<(nm + 127) / 128, 128, 0, st>>>(nm, iters, cg_iters_out, d.n_steps, step);

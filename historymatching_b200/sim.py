@@ -56,7 +56,8 @@ def _is_torch(x):
 
 def run_ensemble(grid: GridSpec, K, well_cell, well_rate, S0, dt, n_steps, *, n_members=None,
                  obs_cell=None, por=None, history=False, pressure=False, want_substeps=False,
-                 cg_rtol=0.0, cg_max_iter=0, chunk_members=0, precond=0, sat_block=0, warm_start=0, ctx=None) -> SimResult:
+                 cg_rtol=0.0, cg_max_iter=0, chunk_members=0, precond=0, mg_switch_iters=0, sat_block=0, warm_start=0,
+                 ctx=None) -> SimResult:
     """Run ``n_steps`` of the simulator for every ensemble member.
 
     K          (M,) shared isotropic; (N,M) isotropic; (N,2,M) anisotropic (Kx, Ky);
@@ -172,6 +173,7 @@ def run_ensemble(grid: GridSpec, K, well_cell, well_rate, S0, dt, n_steps, *, n_
     d.status, d.substeps, d.cg_iters = ptr(res.status), ptr(res.substeps), ptr(res.cg_iters)
     d.cg_rtol, d.cg_max_iter, d.chunk_members = float(cg_rtol), int(cg_max_iter), int(chunk_members)
     d.precond = int(precond)
+    d.mg_switch_iters = int(mg_switch_iters)
     d.sat_block = int(sat_block)
     d.hist_stride = hist_stride
     d.warm_start = int(warm_start)

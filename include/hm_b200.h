@@ -106,6 +106,8 @@ typedef struct hm_sim_desc {
                             *     40 iterations restarts with the FP64 cycle and the rest of the call stays FP64
                             *     (hm_sim_stats.mg_fp64_fallbacks); grids of <= 2048 cells: fused kernel, FP64 cycle;
                             * 1 = Jacobi, 2 = FP64 multigrid W-cycle, 3 = FP32 V-cycle without fallback, 4 = FP64 V-cycle */
+    int32_t mg_switch_iters; /* precond 0: iterations after which a solve switches to the FP64 cycle; <= 0: default (40, and
+                            * 80 for the cold first solve of a call).  A positive value also makes the switch sticky at once. */
     int32_t sat_block;     /* kernel selection.  0 = automatic: grids of <= 2048 cells run the whole simulator in ONE kernel,
                             * one CTA per member (hm_small.cu); larger grids take the streamed path with the cluster
                             * transport kernel (all sub-steps of a time step in one launch) where a member's tiles fit a

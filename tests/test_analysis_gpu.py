@@ -245,3 +245,12 @@ def test_corr_ill_defined_column():
     got = ha.corr(a, b)
     assert np.isnan(got[2]) and np.isnan(ref[2])
     np.testing.assert_allclose(np.delete(got, 2), np.delete(ref, 2), rtol=1e-11)
+
+
+def test_cov_corr_against_reference_golden(golden):
+    """hm_corr against the outputs of the reference's own utils.cov / utils.corr (tests/golden/primitives.npz)."""
+    from historymatching_b200 import analysis as ha
+
+    g = golden("primitives.npz")
+    np.testing.assert_allclose(ha.cov(g["E"], g["b"]), g["cov"], rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(ha.corr(g["E"], g["b"][:, 0]), g["corr"], rtol=1e-11, atol=1e-13)

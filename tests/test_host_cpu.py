@@ -41,6 +41,17 @@ def test_library_exports_every_declared_symbol():
         names += [n.strip().lstrip("*") for n in decl.split()[-1:]] if "," not in decl else [
             n.strip().lstrip("*") for n in re.sub(r"^\s*(const\s+)?\w+\s*\**", "", decl).split(",")]
     assert names == [f[0] for f in _lib.SimDesc._fields_]
+    stats = re.search(r"typedef struct hm_sim_stats \{(.*?)\} hm_sim_stats;", header, flags=re.S).group(1)
+    stats = re.sub(r"/\*.*?\*/", "", stats, flags=re.S)
+    assert re.findall(r"int64_t\s+(\w+)\s*;", stats) == [f[0] for f in _lib.SimStats._fields_]
+
+
+def test_history_rows_of_strided_history():
+    """Row bookkeeping of hm_sim_desc.hist_stride (mirrors hist_rows / hist_row of csrc/hm_sim_common.cuh)."""
+    for n_steps in (1, 4, 6, 7, 40):
+        for k in (2, 3, 5, 50):
+            rows = sorted(set(range(0, n_steps + 1, k)) | {n_steps})
+            assert len(rows) == 1 + -(-n_steps // k)
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -245,16 +245,15 @@ def test_pressure_preconditioners_agree_with_oracle(precond):
     np.testing.assert_allclose(res.S_hist, wsats, rtol=0, atol=SAT_TOL)
 
 
-def test_fp32_cycle_falls_back_to_fp64(monkeypatch):
-    """precond 0: a solve that is still running after HM_MG_SWITCH_ITERS iterations restarts CG with the FP64
+def test_fp32_cycle_falls_back_to_fp64():
+    """precond 0: a solve that is still running after mg_switch_iters iterations restarts CG with the FP64
     cycle (here forced after 2 iterations); the result is unchanged and the rest of the run stays FP64."""
     from historymatching_b200.sim import run_ensemble
 
     m, grid, logk, cells, rates, prd = _setup(64, 48, 3, seed=5)
     dt, nT = 0.025, 3
-    monkeypatch.setenv("HM_MG_SWITCH_ITERS", "2")
     res = run_ensemble(grid, orr.perm_transf(logk), cells, rates, np.zeros(grid.M), dt, nT, obs_cell=prd,
-                       history=True, want_substeps=True)
+                       history=True, want_substeps=True, mg_switch_iters=2)
     assert not res.status.any()
     assert res.stats["mg_fp64_fallbacks"] == 1  # sticky: only the first solve switches
     wsats, _ = _oracle(m, logk, dt, nT, np.zeros(grid.M), prd)
