@@ -68,22 +68,65 @@ def peaks():
 
 # ---- clocks ----------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons during the timed region.  In-process NVML (nvidia_ml_py): spawning nvidia-smi
+    every 0.2 s stalls kernel launches for milliseconds (its NVML start-up takes driver locks), which tripled the
+    measured time of the 14 ms notebook-size workload.  nvidia-smi is the fallback when NVML cannot be loaded."""
+
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.index, self.samples, self.times, self.stop_flag = index, [], [], threading.Event()
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            try:
+                import torch
+
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n, h = self.nvml, self.handle
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = int(get(h))
+        masks = (0x8, 0x40, 0x20, 0x4)  # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+        return [str(sm), str(mx)] + ["Active" if bits & m else "Not Active" for m in masks]
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.samples.append([x.strip() for x in out.strip().split(",")])
+                if self.nvml is not None:
+                    smp = self._sample_nvml()
+                    self.times.append(time.perf_counter())
+                    self.samples.append(smp)
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                    self.times.append(time.perf_counter())
+                    self.samples.append([x.strip() for x in out.strip().split(",")])
             except Exception:
                 pass
             self.stop_flag.wait(0.2)
+
+    def window(self, t0, t1):
+        """Keep the samples taken inside the timed region [t0, t1]; a region shorter than the sampling period keeps
+        the sample nearest to it (the sampler runs from before the warm-up passes, so the GPU is already under load)."""
+        n = min(len(self.times), len(self.samples))
+        inside = [i for i in range(n) if t0 <= self.times[i] <= t1]
+        if not inside and n:
+            inside = [min(range(n), key=lambda i: min(abs(self.times[i] - t0), abs(self.times[i] - t1)))]
+        self.samples = [self.samples[i] for i in inside]
 
     def summary(self):
         sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
@@ -303,13 +346,18 @@ def main():
         torch.cuda.synchronize()
 
     log("inputs ready")
+    # the clock sampler starts before the warm-up: its first NVML queries take driver locks for milliseconds, which
+    # must not land inside a timed region that may itself be only milliseconds long (workload A)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         one_pass(E0)
         torch.cuda.synchronize()
+        # the bookkeeping reductions of the timed loop too: their first call loads a torch kernel module (tens of ms)
+        int(last["res"].cg_iters.sum()), int(last["res"].substeps.sum())
         log("warm-up pass done")
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
+    t_region0 = time.perf_counter()
     l0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -332,8 +380,10 @@ def main():
     torch.cuda.nvtx.range_pop()
     log("timed passes done")
     barrier()
+    t_region1 = time.perf_counter()
     sampler.stop_flag.set()
     sampler.join()
+    sampler.window(t_region0, t_region1)
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
