@@ -56,6 +56,11 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the baseline sample")
     ap.add_argument("--sat-block", type=int, default=0, help="transport kernel variant (hm_sim_desc.sat_block)")
     ap.add_argument("--precond", type=int, default=0, help="pressure preconditioner (hm_sim_desc.precond)")
+    ap.add_argument("--lanes", type=int, default=1,
+                    help="concurrent member shares (host threads / contexts / streams) of a forward run; 0 = automatic: 2 "
+                         "where the cluster transport kernel runs (config C), else 1.  Default 1: with several lanes the "
+                         "per-phase CUDA-event times include the other lane's kernels, which blurs the roofline figures "
+                         "(measured with --lanes 2 at config C: value +3.0 %, e2e +4.6 %, profiles/README.md)")
     return ap.parse_args()
 
 
@@ -330,7 +335,7 @@ def main():
             print(f"[bench +{time.perf_counter() - t_start:7.1f}s] {msg}", file=sys.stderr, flush=True)
 
     def one_pass(E):
-        Eo, res = case.forward(E, want_substeps=True, sat_block=args.sat_block, precond=args.precond)
+        Eo, res = case.forward(E, want_substeps=True, sat_block=args.sat_block, precond=args.precond, lanes=args.lanes)
         last["res"] = res
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
@@ -363,7 +368,7 @@ def main():
     ev0.record()
     phase = dict(setup=0.0, cg=0.0, flux=0.0, saturation=0.0, obs=0.0)
     upd_ms, cg_member_iters, sat_member_substeps = 0.0, 0, 0
-    stats_acc = dict(cg_kernel_launches=0, sat_kernel_launches=0, mg_fp64_fallbacks=0)
+    stats_acc = dict(cg_kernel_launches=0, sat_kernel_launches=0, mg_fp64_fallbacks=0, kernel_launches=0)
     torch.cuda.nvtx.range_push("timed")  # lets ncu select the timed region (--nvtx --nvtx-include "timed/")
     for _ in range(args.steps):
         post, Eo = one_pass(E0)
@@ -389,6 +394,8 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms)
     launches = ctx.launch_count() - l0
+    if int(last["res"].stats.get("lanes", 1)) > 1:  # the lanes launch from their own library contexts
+        launches += stats_acc["kernel_launches"]
     value = N * wl["nTime"] * args.steps / (ms / 1e3)
     bad = int((last["res"].status != 0).sum())
 
@@ -404,7 +411,7 @@ def main():
             E = x_host.to(dev, non_blocking=True)
             pr = pert_host.to(dev, non_blocking=True)
             ob = noisy_host.to(dev, non_blocking=True)
-            Eo, _ = case.forward(E, sat_block=args.sat_block, precond=args.precond)
+            Eo, _ = case.forward(E, sat_block=args.sat_block, precond=args.precond, lanes=args.lanes)
             post = hd.sharded_update(ha.ens_update0, E, Eo, N, obs=ob, perturbs=pr, decorr=dec)
             out_host.copy_(post, non_blocking=True)
             eo_host.copy_(Eo, non_blocking=True)
@@ -501,7 +508,7 @@ def main():
         config=dict(workload=wl["name"], grid=[wl["Nx"], wl["Ny"]], members_per_gpu=N_loc, members=N,
                     nTime=wl["nTime"], p=p, update="ES (one ES-MDA pass, alpha=4)",
                     l2="inputs larger than L2 (working set %.1f GB per GPU)" % (13 * N_loc * M * 8 / 1e9),
-                    parallelism=f"members sharded x{world}"),
+                    parallelism=f"members sharded x{world}", lanes_per_gpu=int(last["res"].stats.get("lanes", 1))),
         update_ms=upd_ms / args.steps,
         phases_ms_per_step={k: v / args.steps for k, v in phase.items()},
         secondary_kernel=dict(kernel=other, achieved=(ob / (ot * 1e-3) / 1e9 if ot > 0 else 0.0), unit="GB/s"),

@@ -54,7 +54,103 @@ def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
 
-def run_ensemble(grid: GridSpec, K, well_cell, well_rate, S0, dt, n_steps, *, n_members=None,
+_LANES: dict = {}  # (device, lane) -> (Context, torch stream): the extra lanes' library contexts and streams
+
+
+def uses_cluster_transport(grid: GridSpec, sat_block=0) -> bool:
+    """Whether hm_sim_batch takes the streamed path with the cluster transport kernel for this grid (the tiling rule of
+    csrc/hm_sim.cu: row tiles of <= 2048 cells, even height, at most 16 tiles per member)."""
+    if sat_block in (1, 5) or (grid.M <= 2048 and sat_block == 0):
+        return False
+    R = max(1, min(grid.Nx, 2048 // grid.Ny))
+    if 1 < R < grid.Nx:
+        R &= ~1
+    return -(-grid.Nx // R) <= 16
+
+
+def run_ensemble(grid: GridSpec, K, well_cell, well_rate, S0, dt, n_steps, *, n_members=None, lanes=1, **kw) -> SimResult:
+    """Run ``n_steps`` of the simulator for every ensemble member (see ``_run_ensemble_one`` for the arguments).
+
+    ``lanes = L > 1`` (device path only): the members are split into L contiguous shares that run concurrently from L
+    host threads, each with its own library context (workspace) and CUDA stream.  The cluster transport kernel can
+    occupy 120 of the 148 SMs and leaves HBM idle, the pressure solve is HBM bound: a second lane fills the gaps
+    (measured at 128^2 x 1024 members: 1.04x with 2 lanes, 1.06x with 4; results bit-identical,
+    profiles/two_lanes_r1.txt).  ``lanes = 0``: 2 where the cluster transport kernel runs and the ensemble has at
+    least 256 members, else 1.  ``stats`` are summed over the lanes (phase times therefore add up to more than the
+    wall time).
+    """
+    use_torch = _is_torch(K)
+    counts = [x.shape[0] for x, nd in ((K, 2), (S0, 2), (well_cell, 2), (well_rate, 3))
+              if hasattr(x, "ndim") and x.ndim >= nd and x.shape[0] > 1]
+    N = n_members or (counts[0] if counts else 1)
+    if lanes == 0:
+        lanes = 2 if (use_torch and N >= 256 and uses_cluster_transport(grid, kw.get("sat_block", 0))) else 1
+    if lanes <= 1 or not use_torch or N < 2 * lanes or kw.get("ctx") is not None:
+        return _run_ensemble_one(grid, K, well_cell, well_rate, S0, dt, n_steps, n_members=n_members, **kw)
+
+    import threading
+
+    import torch
+
+    dev = K.device
+    di = dev.index if dev.index is not None else torch.cuda.current_device()
+    main = torch.cuda.current_stream(di)
+
+    def share(x, nd, lo, hi):  # per-member arrays are sliced, shared ones passed through
+        if hasattr(x, "ndim") and x.ndim >= nd and x.shape[0] == N and N > 1:
+            return x[lo:hi]
+        return x
+
+    bounds = [(N * i // lanes, N * (i + 1) // lanes) for i in range(lanes)]
+    # outputs of the whole ensemble, allocated once; every lane writes its own member range
+    full = _run_ensemble_one(grid, K, well_cell, well_rate, S0, dt, n_steps, n_members=N, _alloc_only=True, **kw)
+    results, errors = [None] * lanes, [None] * lanes
+
+    def work(i):
+        lo, hi = bounds[i]
+        try:
+            torch.cuda.set_device(di)  # a new thread starts on device 0
+            if (di, i) not in _LANES:
+                _LANES[(di, i)] = (_lib.Context(di), torch.cuda.Stream(device=di))
+            ctx, stream = _LANES[(di, i)]
+            stream.wait_stream(main)
+            with torch.cuda.stream(stream):
+                out = SimResult(**{f: (getattr(full, f)[lo:hi] if getattr(full, f) is not None and f != "stats" else None)
+                                   for f in ("S_last", "obs", "S_hist", "P_last", "status", "substeps", "cg_iters")})
+                results[i] = _run_ensemble_one(grid, share(K, 2, lo, hi), share(well_cell, 2, lo, hi),
+                                               share(well_rate, 3, lo, hi), share(S0, 2, lo, hi), dt, n_steps,
+                                               n_members=hi - lo, _out=out, **{**kw, "ctx": ctx})
+        except BaseException as e:  # re-raised in the caller's thread
+            errors[i] = e
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(lanes)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for i in range(lanes):
+        main.wait_stream(_LANES[(di, i)][1]) if (di, i) in _LANES else None
+    for e in errors:
+        if e is not None:
+            raise e
+    stats = {}
+    for r in results:
+        for k, v in r.stats.items():
+            if k == "phase_ms":
+                stats.setdefault(k, {})
+                for ph, ms in v.items():
+                    stats[k][ph] = stats[k].get(ph, 0.0) + ms
+            elif k == "sat_resident_ctas":
+                stats[k] = max(stats.get(k, 0), v)
+            else:
+                stats[k] = stats.get(k, 0) + v
+    stats["lanes"] = lanes
+    full.stats = stats
+    return full
+
+
+def _run_ensemble_one(grid: GridSpec, K, well_cell, well_rate, S0, dt, n_steps, *, n_members=None, _out=None,
+                      _alloc_only=False,
                  obs_cell=None, por=None, history=False, pressure=False, want_substeps=False,
                  cg_rtol=0.0, cg_max_iter=0, chunk_members=0, precond=0, mg_switch_iters=0, sat_block=0, warm_start=0,
                  ctx=None) -> SimResult:
@@ -148,15 +244,20 @@ def run_ensemble(grid: GridSpec, K, well_cell, well_rate, S0, dt, n_steps, *, n_
     if por is not None:
         por = as_f64(por).reshape(-1)
 
-    res = SimResult(S_last=empty((N, M)))
-    res.obs = empty((N, n_steps, n_obs)) if n_obs else None
     hist_stride = int(history) if (history is not True and history) else (1 if history else 0)
     n_hist = n_steps + 1 if hist_stride <= 1 else 1 + -(-n_steps // hist_stride)
-    res.S_hist = empty((N, n_hist, M)) if history else None
-    res.P_last = empty((N, M)) if pressure else None
-    res.status = empty((N,), i32)
-    res.substeps = empty((N, n_steps), i32) if want_substeps else None
-    res.cg_iters = empty((N, n_steps), i32) if want_substeps else None
+    if _out is not None:  # a lane of run_ensemble: views into the outputs of the whole ensemble
+        res = _out
+    else:
+        res = SimResult(S_last=empty((N, M)))
+        res.obs = empty((N, n_steps, n_obs)) if n_obs else None
+        res.S_hist = empty((N, n_hist, M)) if history else None
+        res.P_last = empty((N, M)) if pressure else None
+        res.status = empty((N,), i32)
+        res.substeps = empty((N, n_steps), i32) if want_substeps else None
+        res.cg_iters = empty((N, n_steps), i32) if want_substeps else None
+    if _alloc_only:
+        return res
 
     d = _lib.SimDesc()
     d.n_members, d.Nx, d.Ny, d.Lx, d.Ly = N, grid.Nx, grid.Ny, grid.Lx, grid.Ly
