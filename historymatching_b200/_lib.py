@@ -48,6 +48,7 @@ class SimStats(C.Structure):
     _fields_ = [
         ("cg_iterations", i64), ("sat_substeps", i64), ("kernel_launches", i64),
         ("cg_kernel_launches", i64), ("sat_kernel_launches", i64), ("mg_fp64_fallbacks", i64),
+        ("cg_restarts", i64),
         ("sat_resident_ctas", i64),
     ]
 

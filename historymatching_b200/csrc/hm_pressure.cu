@@ -601,7 +601,7 @@ k_cg_init(Geo g, Wells w, int step, double* __restrict__ X, const double* __rest
           const double* __restrict__ TYl, const double* __restrict__ dinv, const double* __restrict__ pin,
           double* __restrict__ Rv, double* __restrict__ Z, double* __restrict__ part_rz,
           double* __restrict__ part_rr, double* __restrict__ bb, int* __restrict__ done,
-          int* __restrict__ iters, int* __restrict__ counters) {
+          int* __restrict__ iters, int* __restrict__ counters, int init) {
     extern __shared__ double sm[];
     __shared__ int wc[kMaxWells];
     __shared__ double wr[kMaxWells];
@@ -660,7 +660,7 @@ k_cg_init(Geo g, Wells w, int step, double* __restrict__ X, const double* __rest
     if (threadIdx.x == 0) {
         if (JACOBI) part_rz[(int64_t)m * g.nTiles + t] = rz;
         part_rr[(int64_t)m * g.nTiles + t] = rr;
-        if (t == 0) {
+        if (t == 0 && init) {  // init == 0: only the true residual of the current iterate is recomputed
             bb[m] = q2;
             iters[m] = 0;
             const int d = (q2 == 0.0);
@@ -682,7 +682,22 @@ __global__ void k_cg_check(int nm, int nTiles, int k, double tol2, const double*
         done[m] = 1;
         atomicAdd(&counters[0], 1);
     } else {
-        iters[m] = k + 1;
+        iters[m] += 1;  // iterations this member performs (member-local also across a reactivation, see k_cg_reactivate)
+    }
+}
+
+// After a long solve: the recursively updated residual of CG drifts away from the true one (the gap grows with the
+// iteration count and the condition number).  k_cg_init(init = 0) has recomputed r = q - A x; members whose TRUE
+// residual is above the tolerance are reactivated.
+__global__ void k_cg_reactivate(int nm, int nTiles, double tol2, const double* __restrict__ part_rr,
+                                const double* __restrict__ bb, int* __restrict__ done, int* __restrict__ counters) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nm || !done[m]) return;
+    double rr = 0.0;
+    for (int t = 0; t < nTiles; ++t) rr += part_rr[(int64_t)m * nTiles + t];
+    if (rr > tol2 * bb[m]) {
+        done[m] = 0;
+        atomicSub(&counters[0], 1);
     }
 }
 
@@ -1058,10 +1073,10 @@ int pressure_solve(hm_ctx* ctx, const Geo& g, const Wells& w, int step, int nm, 
 
     if (jacobi)
         k_cg_init<true><<<grid, kThreads, smem1, st>>>(g, w, step, P, TXl, TYl, dinv, pin, Rv, Z, part_rz, part_rr,
-                                                        bb, done, iters, counters);
+                                                        bb, done, iters, counters, 1);
     else
         k_cg_init<false><<<grid, kThreads, smem1, st>>>(g, w, step, P, TXl, TYl, dinv, pin, Rv, Z, part_rz, part_rr,
-                                                         bb, done, iters, counters);
+                                                         bb, done, iters, counters, 1);
     ctx->sim_stats.kernel_launches += 1;
     ctx->sim_stats.cg_kernel_launches += 1;
 
@@ -1069,6 +1084,12 @@ int pressure_solve(hm_ctx* ctx, const Geo& g, const Wells& w, int step, int nm, 
     bool all_done = false;
     bool restart = false;  // the next iteration starts a new Krylov space (preconditioner changed): p = z
     const int chk_blocks = (nm + 127) / 128;
+    // Solves that took more than kVerifyIters iterations are verified against the TRUE residual and, if needed,
+    // continued from a restart (at most twice): the residual gap of CG is negligible for the ~15-iteration solves of
+    // the smooth priors and matters for ill-conditioned systems (anisotropic cells, extreme contrast: hundreds of
+    // iterations).  Short solves pay nothing.
+    constexpr int kVerifyIters = 50;
+    for (int round = 0;; ++round) {
     while (k < max_iter && !all_done) {
         const int kend = std::min(max_iter, k + *cg_batch);
         for (; k < kend; ++k) {
@@ -1105,6 +1126,19 @@ int pressure_solve(hm_ctx* ctx, const Geo& g, const Wells& w, int step, int nm, 
         HM_CUDA(cudaMemcpyAsync(ctx->h_pinned, counters, sizeof(int), cudaMemcpyDeviceToHost, st));
         HM_CUDA(cudaStreamSynchronize(st));
         all_done = ctx->h_pinned[0] >= nm;
+    }
+    if (jacobi || !all_done || k < kVerifyIters || k >= max_iter || round >= 2) break;
+    k_cg_init<false><<<grid, kThreads, smem1, st>>>(g, w, step, P, TXl, TYl, dinv, pin, Rv, Z, part_rz, part_rr, bb, done,
+                                                     iters, counters, 0);
+    k_cg_reactivate<<<chk_blocks, 128, 0, st>>>(nm, g.nTiles, tol2, part_rr, bb, done, counters);
+    HM_CUDA(cudaMemcpyAsync(ctx->h_pinned, counters, sizeof(int), cudaMemcpyDeviceToHost, st));
+    HM_CUDA(cudaStreamSynchronize(st));
+    ctx->sim_stats.kernel_launches += 2;
+    ctx->sim_stats.cg_kernel_launches += 2;
+    if (ctx->h_pinned[0] >= nm) break;  // every member's true residual meets the tolerance
+    all_done = false;
+    restart = true;
+    ctx->sim_stats.cg_restarts += 1;
     }
     ctx->sim_stats.cg_iterations += k;
     ctx->sim_stats.kernel_launches += 3 * k + 1;

@@ -294,7 +294,7 @@ def _run_ensemble_one(grid: GridSpec, K, well_cell, well_rate, S0, dt, n_steps, 
     res.stats = dict(
         cg_iterations=st.cg_iterations, sat_substeps=st.sat_substeps,
         kernel_launches=st.kernel_launches, cg_kernel_launches=st.cg_kernel_launches,
-        sat_kernel_launches=st.sat_kernel_launches, mg_fp64_fallbacks=st.mg_fp64_fallbacks, sat_resident_ctas=st.sat_resident_ctas,
+        sat_kernel_launches=st.sat_kernel_launches, mg_fp64_fallbacks=st.mg_fp64_fallbacks, cg_restarts=st.cg_restarts, sat_resident_ctas=st.sat_resident_ctas,
         phase_ms=dict(zip(("setup", "cg", "flux", "saturation", "obs"), list(ph))),
     )
     return res

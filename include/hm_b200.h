@@ -131,6 +131,7 @@ typedef struct hm_sim_stats {
     int64_t cg_kernel_launches;
     int64_t sat_kernel_launches;
     int64_t mg_fp64_fallbacks; /* pressure solves that switched from the FP32 to the FP64 multigrid cycle */
+    int64_t cg_restarts;       /* long pressure solves continued after the check of the true residual */
     int64_t sat_resident_ctas; /* cluster transport kernel: CTAs the GPU holds at once (0: other transport path) */
 } hm_sim_stats;
 

@@ -56,7 +56,11 @@ def _oracle(m, logk, dt, nT, S0, prd):
     (20, 20, 6, 40, 0), (20, 20, 6, 40, 2), (33, 17, 3, 5, 0), (33, 17, 3, 5, 2), (33, 17, 3, 5, 1),
     (45, 45, 2, 3, 0), (26, 30, 2, 4, 0), (64, 64, 2, 3, 0),
     # streaming transport: 1 = bulk-copy staged kernel (even row length), 5 = plain-load kernel
-    (26, 30, 2, 4, 1), (64, 64, 2, 3, 1), (26, 30, 2, 4, 5), (70, 36, 2, 2, 1)])
+    (26, 30, 2, 4, 1), (64, 64, 2, 3, 1), (26, 30, 2, 4, 5), (70, 36, 2, 2, 1),
+    # cluster transport kernel: general (predicated) path, compile-time row length 64, run-time row length 256
+    (100, 100, 2, 2, 0), (96, 64, 2, 2, 0), (40, 256, 2, 2, 0),
+    # streaming kernels on several ragged tiles; vectorised multigrid kernels (row length 128) with a ragged last tile
+    (150, 60, 1, 2, 1), (150, 61, 1, 2, 1), (72, 128, 2, 2, 0)])
 def test_forward_ensemble_matches_oracle(Nx, Ny, N, nT, sat_block):
     from historymatching_b200.sim import run_ensemble
 
@@ -297,7 +301,10 @@ def test_concurrent_lanes_are_bit_identical():
 
     from historymatching_b200.sim import run_ensemble
 
-    m, grid, logk, cells, rates, prd = _setup(64, 64, 7, seed=4)
+    # a mild field: every solve converges within the FP32 cycle and below the verification threshold, so each member's
+    # path is independent of which members share its batch (the FP64 fallback and the true-residual check are taken
+    # per batch; with them the lanes agree to the solver tolerance instead of bit for bit)
+    m, grid, logk, cells, rates, prd = _setup(64, 64, 7, seed=4, rough=0.3)
     K = torch.as_tensor(orr.perm_transf(logk), device="cuda")
     S0 = torch.zeros(grid.M, dtype=torch.float64, device="cuda")
     kw = dict(obs_cell=prd, history=2, pressure=True, want_substeps=True)
@@ -308,6 +315,7 @@ def test_concurrent_lanes_are_bit_identical():
         for f in ("S_last", "obs", "S_hist", "P_last", "status", "substeps", "cg_iters"):
             assert torch.equal(getattr(many, f), getattr(one, f)), f
         assert many.stats["sat_kernel_launches"] == lanes * one.stats["sat_kernel_launches"]
+        assert many.stats["mg_fp64_fallbacks"] == 0 and many.stats["cg_restarts"] == 0
     # per-member wells and initial state are split with the members
     wc = torch.as_tensor(np.tile(cells, (7, 1)), device="cuda")
     wr = torch.as_tensor(np.tile(rates, (7, 1, 1)), device="cuda")
