@@ -470,8 +470,7 @@ def main():
                     share_of_step=t_ms / ms)
     if dom == sat_name and cluster:
         # the cluster kernel touches HBM once per time step (40 B/cell: S in, 3 flux reads incl. pads, S out),
-        # the streaming model above counts 32 B per sub-step: frac > 1 is on-chip reuse, the binding
-        # resource is the FP64 pipe (13 FP64 instructions per cell and sub-step, 64 lanes/clk/SM)
+        # the streaming model above counts 32 B per sub-step: frac > 1 is on-chip reuse
         nts_mean = sat_member_substeps / max(1, N_loc * wl["nTime"] * args.steps)
         sm_hz = (sampler.summary()["sm_mhz"] or 1965.0) * 1e6
         roofline["on_chip_reuse_factor"] = 32.0 * nts_mean / 40.0
