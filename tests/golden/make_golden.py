@@ -134,6 +134,35 @@ def main():
     assert np.allclose(ies, post) and np.allclose(iles, post_loc)
     assert np.allclose(hm["ens_update0_loc"](**gg, obs_ens=Egg, taper=np.ones((d, d))), post)
     np.savez_compressed(os.path.join(OUT, "gauss_gauss.npz"), post=post, post_loc=post_loc, ies=ies, iles=iles, **gg)
+    # ---- observation-error model: the notebook's own cell statements (HistoryMatch.py:243-247, 259) --------------
+    src = open(os.path.join(REF, "HistoryMatch.py")).read()
+    names = {"length_tmp", "corrs1well", "R1well", "R", "R12"}
+    cell = dict(np=np, sla=sla, nTime=40, nPrd=4)
+    for node in ast.parse(src).body:
+        if not isinstance(node, ast.Assign) or len(node.targets) != 1:
+            continue
+        t = node.targets[0]
+        tname = t.id if isinstance(t, ast.Name) else (t.value.id if isinstance(t, ast.Subscript) and isinstance(t.value, ast.Name) else None)
+        if tname in names:
+            exec(compile(ast.Module([node], []), "HistoryMatch.py", "exec"), cell)
+    np.savez_compressed(os.path.join(OUT, "obs_error.npz"), R=cell["R"], R12=cell["R12"], nTime=40, nPrd=4)
+
+    # ---- EnOpt host logic (tools/enopt.py: nabla_ens, backtracker, GD) on a quadratic ----------
+    import tools.enopt as enopt
+
+    utils.nCPU = 1  # serial map: the reference's own code path without pathos
+    target = np.array([1.0, -2.0])
+    obj = lambda u: -np.sum((u - target) ** 2)  # noqa: E731
+    eo = {}
+    for tag, precond in (("lls", False), ("precond", True)):
+        np.random.seed(3)
+        path, objs, info = enopt.GD(obj, np.zeros(2), enopt.nabla_ens(0.1, nEns=12, precond=precond), nIter=6, quiet=True)
+        eo[f"{tag}_path"], eo[f"{tag}_objs"] = np.asarray(path, float), np.asarray(objs, float)
+        eo[f"{tag}_grads"] = np.array([i["grad"] for i in info if "grad" in i])
+    np.random.seed(5)
+    eo["noise_scalar"] = utils.gaussian_noise(4, 3, 0.5)
+    eo["noise_chol"] = utils.gaussian_noise(4, 3, np.linalg.cholesky(np.array([[2.0, 0.3, 0], [0.3, 1, 0.1], [0, 0.1, 0.5]])))
+    np.savez_compressed(os.path.join(OUT, "enopt.npz"), **eo)
     print("golden vectors written to", OUT)
 
 

@@ -257,3 +257,42 @@ def test_enopt_on_quadratic():
     obj = lambda u: -np.sum((u - np.array([1.0, -2.0])) ** 2)  # noqa: E731
     path, objs, info = enopt.GD(obj, np.zeros(2), enopt.nabla_ens(0.1, nEns=12), quiet=True)
     assert np.linalg.norm(path[-1] - [1, -2]) < 0.05 and objs[-1] > objs[0]
+
+
+def test_enopt_matches_reference_golden(golden):
+    """The drop-in tools/enopt.py (nabla_ens, backtracker, GD) and utils.gaussian_noise against the trajectory the
+    reference's own tools/enopt.py produced on the same seed (tests/golden/enopt.npz, make_golden.py)."""
+    from tools import enopt
+
+    g = golden("enopt.npz")
+    utils.nCPU = 1
+    target = np.array([1.0, -2.0])
+    obj = lambda u: -np.sum((u - target) ** 2)  # noqa: E731
+    for tag, precond in (("lls", False), ("precond", True)):
+        np.random.seed(3)
+        path, objs, info = enopt.GD(obj, np.zeros(2), enopt.nabla_ens(0.1, nEns=12, precond=precond), nIter=6, quiet=True)
+        np.testing.assert_array_equal(np.asarray(path, float), g[f"{tag}_path"])
+        np.testing.assert_array_equal(np.asarray(objs, float), g[f"{tag}_objs"])
+        np.testing.assert_array_equal(np.array([i["grad"] for i in info if "grad" in i]), g[f"{tag}_grads"])
+    np.random.seed(5)
+    np.testing.assert_array_equal(utils.gaussian_noise(4, 3, 0.5), g["noise_scalar"])
+    L = np.linalg.cholesky(np.array([[2.0, 0.3, 0], [0.3, 1, 0.1], [0, 0.1, 0.5]]))
+    np.testing.assert_array_equal(utils.gaussian_noise(4, 3, L), g["noise_chol"])
+
+
+def test_workflow_case_matches_notebook_setup(golden):
+    """HistoryMatchCase (the product's packaged notebook set-up): observation-error model equal to the notebook's cell
+    statements (tests/golden/obs_error.npz), wells collocated like ResSim.xy2ind, obs index = well + nPrd * t."""
+    from historymatching_b200.workflow import HistoryMatchCase
+
+    g = golden("obs_error.npz")
+    case = HistoryMatchCase(20, 20, 2.0, 1.0, 0.025, int(g["nTime"]))
+    np.testing.assert_array_equal(case.R, g["R"])
+    np.testing.assert_array_equal(case.R12, g["R12"])
+    np.testing.assert_allclose(case.decorr @ case.R12.T, np.eye(case.p), atol=1e-12)
+    model = simulator.ResSim(Nx=20, Ny=20, Lx=2, Ly=1)
+    near01 = np.array([0.12, 0.87])
+    prd_xy = [[x, y] for y in 1.0 * near01 for x in 2.0 * near01]            # HistoryMatch.py:179-181
+    np.testing.assert_array_equal(case.obs_cell, model.xy2ind(*np.array(prd_xy).T))
+    np.testing.assert_array_equal(case.well_cell[:1], model.xy2ind(1.0, 0.5))
+    assert case.p == 4 * int(g["nTime"]) and case.well_rate.sum() == 0

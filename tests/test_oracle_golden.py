@@ -166,3 +166,12 @@ def test_sim_rejects_unbalanced_and_outside():
         m.sim(0.025, 1, np.zeros(64))
     with pytest.raises(ValueError):
         m.xy2ind(np.array([2.5]), np.array([0.5]))
+
+
+def test_obs_error_model_matches_notebook_cell(golden):
+    """oracle.obs_error_model against the notebook's own statements (HistoryMatch.py:243-247, 259), executed by
+    tests/golden/make_golden.py: the temporally correlated observation-error covariance and its Cholesky factor."""
+    g = golden("obs_error.npz")
+    R, R12 = oa.obs_error_model(int(g["nTime"]), int(g["nPrd"]))
+    np.testing.assert_array_equal(R, g["R"])
+    np.testing.assert_array_equal(R12, g["R12"])
