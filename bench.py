@@ -195,7 +195,11 @@ def run_reference(args, wl, rank):
                 ms_per_step=1e3 * wl["members"] * wl["nTime"] / value, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f64", data="synthetic",
                 config=dict(workload=wl["name"], grid=[wl["Nx"], wl["Ny"]], members_per_gpu=wl["members"],
-                            nTime=wl["nTime"]),
+                            members=wl["members"] * max(1, args.gpus), nTime=wl["nTime"], p=4 * wl["nTime"],
+                            update="ES (one ES-MDA pass, alpha=4)", parallelism=f"members sharded x{max(1, args.gpus)}",
+                            note="the forward run (the part that scales with the ensemble) timed on a bounded sample of "
+                                 "members x steps on the host cores; the ES update of the oracle is timed in the GPU "
+                                 "arm's `update.es_cpu_ms`"),
                 cpu_baseline=dict(value=value, unit="member*steps/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=value, unit="member*steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
