@@ -72,3 +72,47 @@ def test_npv_batches_through_collector():
     om.inj_rates, om.prd_rates = m2.inj_rates, m2.prd_rates
     np.testing.assert_allclose(got, om.sim(dt, nTime, wsat0), rtol=0, atol=1e-8)
     assert m2.actual_rates["inj"].shape == (1, nTime) and m2.actual_rates["prd"].shape == (4, nTime)
+
+
+def test_enopt_gd_on_the_gpu_path():
+    """BASELINE config 5 in miniature: tools.enopt.GD maximises an NPV-like objective over the injector position;
+    the control ensembles of the gradient estimate and the trial steps of the line search run as batched forward
+    runs (utils.nCPU = "auto").  Batched and serial (one member per launch) runs follow the same trajectory."""
+    import historymatching_b200 as hmb
+
+    hmb.activate()
+    import TPFA_ResSim as simulator
+    from tools import enopt, utils
+
+    model = simulator.ResSim(Nx=16, Ny=16, Lx=2, Ly=1)
+    model.K = 0.1 + np.exp(1.2 * np.random.RandomState(5).randn(1, 256))
+    near01 = np.array([0.12, 0.87])
+    model.inj_xy = [[0.5, 0.3]]
+    model.prd_xy = [[x, y] for y in model.Ly * near01 for x in model.Lx * near01]
+    model.inj_rates = np.ones((1, 1))
+    model.prd_rates = np.ones((4, 1)) / 4
+    dt, nTime = 0.025, 5
+
+    def obj(xy):
+        try:
+            m = copy.deepcopy(model)
+            m.inj_xy = xy
+            wsats = m.sim(dt, nTime, np.zeros(m.Nxy), pbar=False)
+            s = wsats[:, m.xy2ind(*m.prd_xy.T)]
+            return float(100 * (dt * m.actual_rates["prd"] * (1 - ((s[:-1] + s[1:]) / 2).T)).sum()
+                         + 30 * wsats[-1].mean())   # produced oil + sweep
+        except Exception:
+            return 0.0
+
+    runs = {}
+    for mode in ("auto", 1):
+        utils.nCPU = mode
+        np.random.seed(11)
+        path, objs, info = enopt.GD(obj, np.array([0.5, 0.3]), enopt.nabla_ens(0.05, nEns=8),
+                                    enopt.backtracker(xSteps=(0.2, 0.1, 0.05), nCPU=3), nIter=3, quiet=True)
+        runs[mode] = (np.asarray(path, float), np.asarray(objs, float))
+    utils.nCPU = 1
+    path, objs = runs["auto"]
+    assert len(objs) >= 2 and np.all(np.diff(objs) > 0)          # every accepted step improves the objective
+    np.testing.assert_allclose(runs[1][1], objs, rtol=1e-9)
+    np.testing.assert_allclose(runs[1][0], path, rtol=1e-9, atol=1e-12)
