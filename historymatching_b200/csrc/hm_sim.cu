@@ -303,10 +303,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 
 constexpr int kStreamThreads = 512;
-constexpr int kStreamCPT = kTileCells / kStreamThreads;
 
-template <bool HAS_POR>
-__global__ void __launch_bounds__(kStreamThreads, 3)
+// CPT cells per thread: 4 (tiles of 2048 cells, ~61 KB, three CTAs per SM) or 8 (tiles of 4096 cells, ~110 KB, two CTAs per
+// SM: the per-CTA prologue - index arithmetic, barrier set-up, halo rows - is amortised over twice the cells and
+// the halo rows are 2 in 8 + 2 instead of 2 in 4 + 2 rows of S).  The Geo passed in carries the matching R / nTiles.
+template <bool HAS_POR, int CPT>
+__global__ void __launch_bounds__(kStreamThreads, CPT == 4 ? 3 : 2)
 k_sat_stream(Geo g, Fluid fl, Wells w, int step, int it, double dt, const int* __restrict__ nts,
              const double* __restrict__ Sin, double* __restrict__ Sout, const double* __restrict__ Vxl,
              const double* __restrict__ Vyl, const double* __restrict__ por) {
@@ -355,10 +357,10 @@ k_sat_stream(Geo g, Fluid fl, Wells w, int step, int it, double dt, const int* _
     __syncthreads();
     mbar_wait(bar, 0);
     // S -> fw(S) in place; a thread keeps the saturation of its own cells
-    double s[kStreamCPT];
+    double s[CPT];
     double* fwp = Ss + Ny + threadIdx.x;
 #pragma unroll
-    for (int j = 0; j < kStreamCPT; ++j) {
+    for (int j = 0; j < CPT; ++j) {
         s[j] = 0.0;
         if (threadIdx.x + j * NT < nInt) {
             s[j] = fwp[j * NT];
@@ -375,7 +377,7 @@ k_sat_stream(Geo g, Fluid fl, Wells w, int step, int it, double dt, const int* _
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < kStreamCPT; ++j) {
+    for (int j = 0; j < CPT; ++j) {
         const int e = threadIdx.x + j * NT;
         if (e < nInt) {
             const double vxl = Vxs[e], vyl = Vys[e], vxh = Vxs[e + Ny], vyh = Vys[e + 1];
@@ -835,11 +837,30 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
 
     // streaming transport (grids whose tiles do not fit a cluster, or sat_block 1): bulk-copy staged kernel when the
     // row length is even (16-byte copies), sat_block 5 forces the plain-load kernel
-    const size_t smem_stream = ((size_t)(3 * g.R + 3) * d.Ny + 2) * sizeof(double);
-    const bool use_stream_tma = d.sat_block != 5 && d.Ny % 2 == 0 && smem_stream <= 75 * 1024;
+    auto stream_geo = [&](int tile_cells) {
+        Geo gs = g;
+        gs.R = std::max(1, std::min(d.Nx, tile_cells / d.Ny));
+        if (gs.R < d.Nx && gs.R > 1) gs.R &= ~1;
+        gs.nTiles = (d.Nx + gs.R - 1) / gs.R;
+        return gs;
+    };
+    auto stream_smem = [&](const Geo& gs) { return ((size_t)(3 * gs.R + 3) * d.Ny + 2) * sizeof(double); };
+    // 4096-cell tiles (8 cells per thread, 2 CTAs per SM) where they fit; sat_block 6 forces the 2048-cell tiles
+    Geo gs = stream_geo(8 * kStreamThreads);
+    int stream_cpt = 8;
+    if (d.sat_block == 6 || stream_smem(gs) > 112 * 1024 || gs.nTiles == 1) {
+        gs = stream_geo(4 * kStreamThreads);
+        stream_cpt = 4;
+    }
+    const size_t smem_stream = stream_smem(gs);
+    const bool use_stream_tma = d.sat_block != 5 && d.Ny % 2 == 0 && smem_stream <= 112 * 1024 &&
+                                (int64_t)gs.R * d.Ny <= (int64_t)stream_cpt * kStreamThreads;
+    const int grid_stream = nm * gs.nTiles;
     if (use_stream_tma) {
-        HM_CUDA(cudaFuncSetAttribute(k_sat_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream));
-        HM_CUDA(cudaFuncSetAttribute(k_sat_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream));
+        HM_CUDA(cudaFuncSetAttribute(k_sat_stream<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream));
+        HM_CUDA(cudaFuncSetAttribute(k_sat_stream<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream));
+        HM_CUDA(cudaFuncSetAttribute(k_sat_stream<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream));
+        HM_CUDA(cudaFuncSetAttribute(k_sat_stream<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream));
     }
 
     // initial state: S <- S0, P <- 0 (cold start of the first solve), flags
@@ -918,12 +939,10 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
         } else {
             for (int it = 0; it < max_nts; ++it, ++sat_launches) {
                 if (use_stream_tma) {
-                    if (d.por)
-                        k_sat_stream<true><<<grid, kStreamThreads, smem_stream, st>>>(g, fl, w, step, it, d.dt, nts, Scur,
-                                                                                     Snxt, Vxl, Vyl, d.por);
-                    else
-                        k_sat_stream<false><<<grid, kStreamThreads, smem_stream, st>>>(g, fl, w, step, it, d.dt, nts, Scur,
-                                                                                      Snxt, Vxl, Vyl, nullptr);
+                    auto ks = d.por ? (stream_cpt == 8 ? k_sat_stream<true, 8> : k_sat_stream<true, 4>)
+                                    : (stream_cpt == 8 ? k_sat_stream<false, 8> : k_sat_stream<false, 4>);
+                    ks<<<grid_stream, kStreamThreads, smem_stream, st>>>(gs, fl, w, step, it, d.dt, nts, Scur, Snxt, Vxl, Vyl,
+                                                                        d.por);
                 } else if (d.por)
                     k_sat_substep<true><<<grid, kThreads, smem1, st>>>(g, fl, w, step, it, d.dt, nts, Scur, Snxt,
                                                                         Vxl, Vyl, d.por);

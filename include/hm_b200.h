@@ -115,7 +115,8 @@ typedef struct hm_sim_desc {
                             * transport kernel (one sub-step per launch).  2 = streamed path, cluster transport kernel.
                             * The streaming kernel stages its tile with bulk copies (cp.async.bulk) when Ny is even.
                             * 4 = as 2 with tiles of 1024 cells, 512 threads, two CTAs per SM (measured: same speed).
-                            * 5 = as 1 with the plain-load streaming kernel. */
+                            * 5 = as 1 with the plain-load streaming kernel.  6 = as 1 with 2048-cell tiles (default: 4096
+                            * cells, 8 per thread, where the tile fits 110 KB of shared memory). */
     int32_t hist_stride;   /* <= 1: S_hist holds every step (the reference's ResSim.sim output); k > 1: every k-th step and
                             * the last one - the saturation history of a large ensemble for plotting / animation cells
                             * (HistoryMatch.py:233, 1212-1214) without n_steps+1 fields per member */

@@ -60,7 +60,7 @@ def _oracle(m, logk, dt, nT, S0, prd):
     # cluster transport kernel: general (predicated) path, compile-time row length 64, run-time row length 256
     (100, 100, 2, 2, 0), (96, 64, 2, 2, 0), (40, 256, 2, 2, 0),
     # streaming kernels on several ragged tiles; vectorised multigrid kernels (row length 128) with a ragged last tile
-    (150, 60, 1, 2, 1), (150, 61, 1, 2, 1), (72, 128, 2, 2, 0)])
+    (150, 60, 1, 2, 1), (150, 61, 1, 2, 1), (72, 128, 2, 2, 0), (150, 60, 1, 2, 6), (64, 64, 2, 3, 6)])
 def test_forward_ensemble_matches_oracle(Nx, Ny, N, nT, sat_block):
     from historymatching_b200.sim import run_ensemble
 
