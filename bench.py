@@ -170,11 +170,18 @@ def cpu_forward_sample(wl, seconds, seed=0):
     members = cores if per * nT * 1.0 < seconds else max(1, int(cores * seconds / (per * nT)))
     members = max(1, min(members, cores * max(1, int(seconds / (per * nT)))))
     logk = geostat.gaussian_fields_separable(grid, members, r=0.8, rng=np.random.RandomState(seed))
+    # hard wall-clock guard: the sample is sized from a cost model, and a 512^2 member-step is about a minute per core
+    limit = max(60.0, 12.0 * seconds)
     with mp.get_context("fork").Pool(cores) as pool:
-        pool.map(_cpu_member, [(grid.Nx, grid.Ny, logk[0], 0.025, 1)] * cores)  # warm the workers
-        t0 = time.perf_counter()
-        pool.map(_cpu_member, [(grid.Nx, grid.Ny, lk, 0.025, nT) for lk in logk], chunksize=1)
-        dt = time.perf_counter() - t0
+        try:
+            warm = (grid.Nx, grid.Ny, logk[0], 0.025, 1) if grid.M <= 20000 else (20, 20, np.zeros(400), 0.025, 1)
+            pool.map_async(_cpu_member, [warm] * cores).get(timeout=limit)  # warm the workers (imports, first solve)
+            t0 = time.perf_counter()
+            pool.map_async(_cpu_member, [(grid.Nx, grid.Ny, lk, 0.025, nT) for lk in logk], chunksize=1).get(timeout=limit)
+            dt = time.perf_counter() - t0
+        except mp.TimeoutError:
+            pool.terminate()
+            return None, cores, f"CPU sample ({members} members x {nT} steps of the {grid.Nx}x{grid.Ny} forward run) did not finish within {limit:.0f} s"
     return members * nT / dt, cores, f"{members} members x {nT} steps of the {grid.Nx}x{grid.Ny} forward run, oracle (scipy spsolve + explicit upwind), one process per core, BLAS pinned to 1 thread"
 
 
@@ -187,8 +194,11 @@ def run_reference(args, wl, rank):
     per_step = max(5.0, min(args.cpu_seconds, 240.0 / max(1, args.steps + args.warmup)))
     for i in range(args.warmup + args.steps):
         v, cores, sample = cpu_forward_sample(wl, per_step, seed=i)
-        if i >= args.warmup:
+        if i >= args.warmup and v is not None:
             vals.append(v)
+    if not vals:
+        print(json.dumps(dict(impl="reference", unavailable=sample)))
+        return
     value = float(np.mean(vals))
     line = dict(metric="ensemble forward-sim member*steps/s", value=value, unit="member*steps/s", impl="reference",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
