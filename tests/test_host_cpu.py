@@ -296,3 +296,36 @@ def test_workflow_case_matches_notebook_setup(golden):
     np.testing.assert_array_equal(case.obs_cell, model.xy2ind(*np.array(prd_xy).T))
     np.testing.assert_array_equal(case.well_cell[:1], model.xy2ind(1.0, 0.5))
     assert case.p == 4 * int(g["nTime"]) and case.well_rate.sum() == 0
+
+
+def test_header_is_plain_c_and_matches_the_ctypes_mirrors(tmp_path):
+    """include/hm_b200.h compiles as strict C99, a C program links against libhm_b200.so, and the struct sizes the C
+    compiler sees equal the ctypes mirrors (the boundary a non-Python host would bind)."""
+    import shutil
+    import subprocess
+
+    from historymatching_b200 import _lib
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    _lib.load()
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "hm_b200.h"\n'
+        "int main(void) {\n"
+        "    hm_sim_desc d; hm_sim_stats st; hm_ctx* ctx = NULL;\n"
+        "    memset(&d, 0, sizeof d); memset(&st, 0, sizeof st);\n"
+        "    int rc = hm_ctx_create(0, &ctx);\n"
+        '    printf("%d %d %zu %zu\\n", hm_version(), rc, sizeof d, sizeof st);\n'
+        "    if (rc == 0) hm_ctx_destroy(ctx);\n"
+        "    return 0;\n}\n")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = tmp_path / "abi"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(exe), "-L", libdir, "-lhm_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    version, rc, size_desc, size_stats = map(int, subprocess.run([str(exe)], capture_output=True, text=True,
+                                                                  check=True).stdout.split())
+    assert version >= 100
+    assert rc in (0, -4)  # HM_OK on a GPU box, HM_ERR_NO_DEVICE here: never a silent CPU path
+    assert size_desc == ctypes.sizeof(_lib.SimDesc) and size_stats == ctypes.sizeof(_lib.SimStats)
