@@ -175,3 +175,34 @@ def test_obs_error_model_matches_notebook_cell(golden):
     R, R12 = oa.obs_error_model(int(g["nTime"]), int(g["nPrd"]))
     np.testing.assert_array_equal(R, g["R"])
     np.testing.assert_array_equal(R12, g["R12"])
+
+
+def test_sim_converges_to_buckley_leverett():
+    """Known answer independent of the (absent) simulator package: 1-D displacement with quadratic relative
+    permeabilities and unit viscosity ratio has the Buckley-Leverett solution - a rarefaction behind a shock of
+    height 1/sqrt(2) moving at f(s*)/s* = 1.2071 pore volumes per unit time.  The restated scheme (first-order
+    upwind, CFL sub-stepped, sequential splitting) must converge to it: front position and L1 error shrink with h,
+    mass is conserved exactly."""
+    from scipy.optimize import brentq
+
+    def run(Nx, T=0.5, nT=10):
+        m = orr.OracleResSim(Nx=Nx, Ny=2, Lx=1.0, Ly=1.0)   # two identical rows: a 1-D flow
+        m.K = np.ones((2, Nx, 2))
+        hx = 1.0 / Nx
+        m.inj_xy = np.array([[hx / 2, 0.25], [hx / 2, 0.75]])
+        m.prd_xy = np.array([[1 - hx / 2, 0.25], [1 - hx / 2, 0.75]])
+        m.inj_rates = m.prd_rates = np.array([[0.5], [0.5]])
+        S = m.sim(T / nT, nT, np.zeros(2 * Nx))[-1].reshape(Nx, 2)
+        assert np.abs(S[:, 0] - S[:, 1]).max() < 1e-8
+        x = (np.arange(Nx) + 0.5) * hx
+        df = lambda s: 2 * s * (1 - s) / (s * s + (1 - s) ** 2) ** 2          # noqa: E731
+        s_shock = 1 / np.sqrt(2)
+        v_shock = (s_shock**2 / (s_shock**2 + (1 - s_shock) ** 2)) / s_shock
+        exact = np.array([brentq(lambda s: df(s) - xi, s_shock, 1.0) if xi < v_shock else 0.0 for xi in x / T])
+        front = x[np.argmax(S[:, 0] < 0.35)]
+        return abs(front - v_shock * T), np.abs(S[:, 0] - exact).mean(), S[:, 0].sum() * hx
+
+    e100, e200 = run(100), run(200)
+    assert e100[0] < 0.02 and e200[0] < 0.012 and e200[0] < e100[0]      # front position converges
+    assert e100[1] < 0.02 and e200[1] < 0.009 and e200[1] < 0.6 * e100[1]   # L1 error converges
+    assert abs(e100[2] - 0.5) < 1e-10 and abs(e200[2] - 0.5) < 1e-10     # injected volume = t * rate

@@ -322,3 +322,30 @@ def test_concurrent_lanes_are_bit_identical():
     S0m = torch.zeros(7, grid.M, dtype=torch.float64, device="cuda")
     per = run_ensemble(grid, K, wc, wr, S0m, 0.025, 3, lanes=2, **kw)
     assert torch.equal(per.S_last, one.S_last)
+
+
+@pytest.mark.parametrize("sat_block", [0, 2])
+def test_buckley_leverett_known_answer(sat_block):
+    """The CUDA path against an answer that does not come from the oracle: the Buckley-Leverett profile of a 1-D
+    displacement (tests/test_oracle_golden.py::test_sim_converges_to_buckley_leverett), on the fused and the streamed path."""
+    from scipy.optimize import brentq
+
+    from historymatching_b200.sim import GridSpec, run_ensemble
+
+    Nx, T, nT = 200, 0.5, 10
+    hx = 1.0 / Nx
+    grid = GridSpec(Nx=Nx, Ny=2, Lx=1.0, Ly=1.0)
+    cells = np.array([0, 1, 2 * (Nx - 1), 2 * (Nx - 1) + 1], np.int32)     # injectors in row 0, producers in the last row
+    rates = np.array([0.5, 0.5, -0.5, -0.5])
+    res = run_ensemble(grid, np.ones(grid.M), cells, rates, np.zeros(grid.M), T / nT, nT, sat_block=sat_block)
+    assert not res.status.any()
+    S = res.S_last[0].reshape(Nx, 2)
+    assert np.abs(S[:, 0] - S[:, 1]).max() < 1e-8
+    x = (np.arange(Nx) + 0.5) * hx
+    df = lambda s: 2 * s * (1 - s) / (s * s + (1 - s) ** 2) ** 2              # noqa: E731
+    s_shock = 1 / np.sqrt(2)
+    v_shock = (s_shock**2 / (s_shock**2 + (1 - s_shock) ** 2)) / s_shock
+    exact = np.array([brentq(lambda s: df(s) - xi, s_shock, 1.0) if xi < v_shock else 0.0 for xi in x / T])
+    assert np.abs(S[:, 0] - exact).mean() < 0.009                           # first-order upwind at h = 1/200
+    assert abs(x[np.argmax(S[:, 0] < 0.35)] - v_shock * T) < 0.012
+    assert abs(S[:, 0].sum() * hx - T) < 1e-10                              # injected volume
