@@ -202,6 +202,16 @@ def test_sim_converges_to_buckley_leverett():
         front = x[np.argmax(S[:, 0] < 0.35)]
         return abs(front - v_shock * T), np.abs(S[:, 0] - exact).mean(), S[:, 0].sum() * hx
 
+    # Darcy's law for the initial state (S = 0: total mobility 1): a unit Darcy velocity needs dP/dx = -1 exactly
+    m = orr.OracleResSim(Nx=50, Ny=2, Lx=1.0, Ly=1.0)
+    m.K = np.ones((2, 50, 2))
+    m.inj_xy, m.prd_xy = np.array([[0.01, 0.25], [0.01, 0.75]]), np.array([[0.99, 0.25], [0.99, 0.75]])
+    m.inj_rates = m.prd_rates = np.array([[0.5], [0.5]])
+    P, Vx, Vy = m.pressure_step(np.zeros(100), m.source_field(0))
+    np.testing.assert_allclose(np.diff(P, axis=0), -1.0 / 50, rtol=1e-10)
+    np.testing.assert_allclose(Vx[1:-1], 0.5, rtol=1e-10)
+    assert np.abs(Vy).max() < 1e-12
+
     e100, e200 = run(100), run(200)
     assert e100[0] < 0.02 and e200[0] < 0.012 and e200[0] < e100[0]      # front position converges
     assert e100[1] < 0.02 and e200[1] < 0.009 and e200[1] < 0.6 * e100[1]   # L1 error converges
