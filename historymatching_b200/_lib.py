@@ -41,6 +41,7 @@ class SimDesc(C.Structure):
         ("status", C.c_void_p), ("substeps", C.c_void_p), ("cg_iters", C.c_void_p),
         ("cg_rtol", C.c_double), ("cg_max_iter", C.c_int32),
         ("chunk_members", C.c_int32), ("precond", C.c_int32), ("mg_switch_iters", C.c_int32), ("sat_block", C.c_int32), ("hist_stride", C.c_int32), ("warm_start", C.c_int32),
+        ("tb_cluster_rows", C.c_int32), ("tb_halo", C.c_int32),
     ]
 
 
@@ -50,6 +51,7 @@ class SimStats(C.Structure):
         ("cg_kernel_launches", i64), ("sat_kernel_launches", i64), ("mg_fp64_fallbacks", i64),
         ("cg_restarts", i64),
         ("sat_resident_ctas", i64),
+        ("sat_tb_cluster", i64), ("sat_tb_strips", i64), ("sat_tb_halo", i64), ("sat_cell_updates", i64),
     ]
 
 
@@ -95,11 +97,11 @@ def load(build_if_missing: bool = True):
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
-            if not build_if_missing:
-                raise HmError(f"{LIB_PATH} not found (run python -m historymatching_b200.build)")
-            from . import build as _build
+        from . import build as _build
 
+        if _build.needs_build():  # missing, or built from other sources than the tree's (content hash)
+            if not build_if_missing:
+                raise HmError(f"{LIB_PATH} is missing or stale (run python -m historymatching_b200.build)")
             _build.build()
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SYMBOLS.items():

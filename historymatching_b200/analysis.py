@@ -42,9 +42,12 @@ def _torch():
 def _dev(x, like=None):
     """float64 contiguous CUDA tensor of x (copying numpy input to the device)."""
     torch = _torch()
+    dev = like.device if like is not None else None  # follow the ensemble's GPU, not the current device
     if isinstance(x, torch.Tensor):
-        return x.to(device="cuda" if x.device.type != "cuda" else x.device, dtype=torch.float64).contiguous()
-    return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device="cuda")
+        if dev is None:
+            dev = x.device if x.device.type == "cuda" else "cuda"
+        return x.to(device=dev, dtype=torch.float64).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device=dev if dev is not None else "cuda")
 
 
 def _back(t, was_numpy):
@@ -118,7 +121,7 @@ def ens_update0(prior_ens, obs_ens, obs, perturbs, decorr):
     """ES analysis update; see ``HistoryMatch.py:578-586``."""
     was_np = not _is_tensor(prior_ens)
     E = _dev(prior_ens).clone()
-    Eo, y, pert, dec = _dev(obs_ens), _dev(obs), _dev(perturbs), _dev(decorr)
+    Eo, y, pert, dec = _dev(obs_ens, E), _dev(obs, E), _dev(perturbs, E), _dev(decorr, E)
     N, M = E.shape
     p = y.shape[0]
     assert Eo.shape == (N, p) and pert.shape == (N, p) and dec.shape == (p, p)
@@ -131,7 +134,8 @@ def bump_taper(xy_prm, xy_obs, radius, sharpness=1.0):
     """``loc.bump(loc.pairwise_distances(xy_prm, xy_obs) / radius, sharpness)``
     (``tools/localization.py:9-92``, ``HistoryMatch.py:717,863``) on the device."""
     was_np = not _is_tensor(xy_prm)
-    a, b = _dev(xy_prm), _dev(xy_obs)
+    a = _dev(xy_prm)
+    b = _dev(xy_obs, a)
     assert a.shape[1] == 2 and b.shape[1] == 2
     torch = _torch()
     out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float64, device=a.device)
@@ -145,7 +149,7 @@ def ens_update0_loc(prior_ens, obs_ens, obs, perturbs, decorr, taper):
     """Localised ES update; see ``HistoryMatch.py:774-797``."""
     was_np = not _is_tensor(prior_ens)
     E = _dev(prior_ens).clone()
-    Eo, y, pert, dec, tap = _dev(obs_ens), _dev(obs), _dev(perturbs), _dev(decorr), _dev(taper)
+    Eo, y, pert, dec, tap = _dev(obs_ens, E), _dev(obs, E), _dev(perturbs, E), _dev(decorr, E), _dev(taper, E)
     N, M = E.shape
     p = y.shape[0]
     assert tap.shape == (M, p)
@@ -173,7 +177,7 @@ def IES(prior_ens, obs_ens, obs, perturbs, decorr, xStep=1.0, iMax=4):
     was_np = not _is_tensor(prior_ens)
     stats = Stats(E=[], Eo=[])
     E0 = _dev(prior_ens)
-    y, pert, dec = _dev(obs), _dev(perturbs), _dev(decorr)
+    y, pert, dec = _dev(obs, E0), _dev(perturbs, E0), _dev(decorr, E0)
     N, M = E0.shape
     p = y.shape[0]
     ctx = _ctx(E0)
@@ -186,7 +190,7 @@ def IES(prior_ens, obs_ens, obs, perturbs, decorr, xStep=1.0, iMax=4):
         Eo = obs_ens(_back(E, was_np))
         stats.E.append(_back(E, was_np))
         stats.Eo.append(Eo)
-        Eo_d = _dev(Eo)
+        Eo_d = _dev(Eo, E0)
         assert Eo_d.shape == (N, p)
         ctx.use_torch_stream()
         _lib.check(ctx.lib.hm_ies_step(ctx.handle, N, p, _p(W), _p(Eo_d), _p(y), _p(pert), _p(dec), float(xStep)))
@@ -204,7 +208,7 @@ def ILES(prior_ens, obs_ens, obs, perturbs, decorr, taper, xStep=1.0, iMax=4):
     was_np = not _is_tensor(prior_ens)
     stats = Stats(E=[], Eo=[])
     E0 = _dev(prior_ens)
-    y, pert, dec, tap = _dev(obs), _dev(perturbs), _dev(decorr), _dev(taper)
+    y, pert, dec, tap = _dev(obs, E0), _dev(perturbs, E0), _dev(decorr, E0), _dev(taper, E0)
     N, M = E0.shape
     p = y.shape[0]
     assert tap.shape == (M, p)
@@ -224,7 +228,7 @@ def ILES(prior_ens, obs_ens, obs, perturbs, decorr, taper, xStep=1.0, iMax=4):
         Eo = obs_ens(_back(E, was_np))
         stats.E.append(_back(E, was_np))
         stats.Eo.append(Eo)
-        Eo_d = _dev(Eo)
+        Eo_d = _dev(Eo, E0)
         assert Eo_d.shape == (N, p)
         ctx.use_torch_stream()
         _lib.check(ctx.lib.hm_iles_step(ctx.handle, N, M, p, _p(Ws), _p(Eo_d), _p(y), _p(pert), _p(dec), _p(tap),
@@ -259,5 +263,5 @@ def es_mda(prior_ens, obs_ens, obs, R12, alphas, decorr=None, perturbs=None):
         stats.E.append(_back(E, was_np))
         stats.Eo.append(Eo)
         Z = np.random.randn(N, p) if perturbs is None else np.asarray(perturbs[i])
-        E = ens_update0(E, _dev(Eo), obs, np.sqrt(a) * (Z @ R12.T), decorr / np.sqrt(a))
+        E = ens_update0(E, _dev(Eo, E), obs, np.sqrt(a) * (Z @ R12.T), decorr / np.sqrt(a))
     return _back(E, was_np), stats

@@ -16,9 +16,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhm_b200.so")
-SOURCES = ["hm_api.cu", "hm_sim.cu", "hm_pressure.cu", "hm_small.cu", "hm_gemm.cu", "hm_analysis.cu"]
+SOURCES = ["hm_api.cu", "hm_sim.cu", "hm_transport.cu", "hm_pressure.cu", "hm_small.cu", "hm_gemm.cu", "hm_analysis.cu"]
 HEADERS = [os.path.join(CSRC, "hm_common.cuh"), os.path.join(CSRC, "hm_sim_common.cuh"),
-           os.path.join(CSRC, "hm_mg_onchip.cuh"),
+           os.path.join(CSRC, "hm_mg_onchip.cuh"), os.path.join(CSRC, "hm_ptx.cuh"),
            os.path.join(HERE, "..", "include", "hm_b200.h")]
 
 
@@ -29,25 +29,51 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found: libhm_b200.so cannot be built")
 
 
+STAMP = LIB + ".stamp"
+
+
+def source_hash() -> str:
+    """Hash of every source and header the library is built from (mtimes do not survive a repo snapshot)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for path in [os.path.join(CSRC, s) for s in SOURCES] + HEADERS:
+        with open(path, "rb") as f:
+            h.update(os.path.basename(path).encode() + b"\0" + f.read())
+    h.update(os.environ.get("HM_NVCC_EXTRA", "").encode())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    """True when the library is missing or was built from other sources than the ones in the tree."""
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
+    import fcntl
+
+    with open(LIB + ".lock", "w") as lock:  # one builder at a time (several ranks may start together)
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not needs_build():
+            return LIB
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose: bool) -> str:
     cuda_lib = os.path.join(os.path.dirname(os.path.dirname(nvcc_path())), "lib64")
+    tmp = LIB + ".tmp"
     cmd = [
         nvcc_path(),
         "-gencode", "arch=compute_100a,code=sm_100a",
         "-O3", "-std=c++17", "-lineinfo", *os.environ.get("HM_NVCC_EXTRA", "").split(),
         "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
         "-shared",
-        "-o", LIB,
+        "-o", tmp,
         *[os.path.join(CSRC, s) for s in SOURCES],
         f"-L{cuda_lib}", "-lcusolver",
         "-Xlinker", f"-rpath={cuda_lib}",
@@ -60,6 +86,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stdout + res.stderr)
+    os.replace(tmp, LIB)
+    with open(STAMP, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB
 
 

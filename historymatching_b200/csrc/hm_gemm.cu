@@ -156,11 +156,8 @@ int launch(hm_ctx* ctx, const Operand& A, const Operand& B, int64_t K, double al
            double* C, int64_t ldc) {
     constexpr int BM = 32 * WM, BN = 32 * WN;
     const size_t smem = (size_t)2 * (BM + BN) * LDS * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
-        HM_CUDA(cudaFuncSetAttribute(k_dgemm<WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    // per launch: the attribute belongs to the current device's context (a process may drive several GPUs)
+    HM_CUDA(cudaFuncSetAttribute(k_dgemm<WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((B.rows + BN - 1) / BN), (unsigned)((A.rows + BM - 1) / BM));
     k_dgemm<WM, WN><<<grid, WM * WN * 32, smem, ctx->stream>>>(A, B, K, alpha, beta, C, ldc);
     HM_CUDA(cudaGetLastError());

@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <type_traits>
 
+#include "hm_ptx.cuh"
 #include "hm_sim_common.cuh"
 
 using namespace hmsim;
@@ -35,6 +36,10 @@ int pressure_solve(hm_ctx* ctx, const Geo& g, const Wells& w, int step, int nm, 
                    int* cg_batch, int* iters_used, bool* all_done_out);
 int sim_small_supported(const hm_sim_desc& d);
 int sim_small(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm);
+bool transport_tb_supported(const hm_sim_desc& d);
+int transport_tb(hm_ctx* ctx, const hm_sim_desc& d, const Fluid& fl, const Wells& w, int step, int nm, int max_nts,
+                 const int* nts, double* Scur, double* Snxt, const double* Vxl, const double* Vyl, double** Sresult,
+                 int* launches);
 }
 
 namespace {
@@ -263,32 +268,6 @@ k_sat_substep(Geo g, Fluid fl, Wells w, int step, int it, double dt, const int* 
 // the RECEIVING CTA); the receiver posts the expected byte count on that mbarrier and waits on its
 // phase.  (A cluster barrier per sub-step costs a GPU-scope MEMBAR plus an L1 invalidate, CCTL.IVALL,
 // on this architecture and dominated the sub-step.)
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, int cta_rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, int bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, int parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_bar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
-                 "l"(__double_as_longlong(v)), "r"(remote_bar) : "memory");
-}
-
 // ---- K4c: streaming sub-step with bulk-copy (TMA) staging -------------------------------------------------
 // Same arithmetic and traffic as k_sat_substep, different data movement.  k_sat_substep is bound by memory
 // latency (ncu at 512^2: long-scoreboard stalls, 48 % of the DRAM peak): a thread first waits for its S values,
@@ -297,11 +276,6 @@ __device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uin
 // the x-fluxes of R+1 rows, the y-fluxes (+ one element) - ~61 KB in flight per CTA, three CTAs per SM; the
 // CTA then turns S into fw(S) in place (own cells keep S in registers), and applies the stencil from shared
 // memory.  Needs an even row length (16-byte granularity of the bulk copies).
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
 constexpr int kStreamThreads = 512;
 
 // CPT cells per thread: 4 (tiles of 2048 cells, ~61 KB, three CTAs per SM) or 8 (tiles of 4096 cells, ~110 KB, two CTAs per
@@ -342,6 +316,7 @@ k_sat_stream(Geo g, Fluid fl, Wells w, int step, int it, double dt, const int* _
         bulk_g2s(smem_u32(Vxs), Vxl + base, bX, bar);
         bulk_g2s(smem_u32(Vys), Vyl + base, bY, bar);
     }
+    __syncwarp();  // lanes 1-31 of warp 0 poll the barrier below: not before lane 0 has initialised it
     if (w.n > 0) load_wells(w, m, step, wc, wr);
     // halo rows outside the domain: zero (the matching flux is zero, the value only has to be finite); the bulk
     // copies do not touch these rows
@@ -409,14 +384,6 @@ k_sat_stream(Geo g, Fluid fl, Wells w, int step, int it, double dt, const int* _
         if (HAS_POR) dtx = dts / (g.h2 * por[c]);
         Sout[base + e] += fma(dtx * fmin(q, 0.0), Ss[Ny + e], fmax(q, 0.0) * dtx);
     }
-}
-
-// predicated form: no branch (and no convergence barrier) around the store in the sub-step loop
-__device__ __forceinline__ void st_async_f64_if(bool pred, uint32_t remote_addr, double v, uint32_t remote_bar) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\t"
-        "@p st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];\n\t}" ::"r"(remote_addr),
-        "l"(__double_as_longlong(v)), "r"(remote_bar), "r"((int)pred) : "memory");
 }
 
 template <bool HAS_POR, int NT, int CPT, int NY>
@@ -817,7 +784,9 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
         gc.R = 1024 / d.Ny;
         gc.nTiles = d.Nx / gc.R;
     }
-    const bool use_cluster = d.sat_block != 1 && d.sat_block != 5 && gc.nTiles <= 16;
+    // temporally blocked kernel (hm_transport.cu): the default where the grid qualifies
+    const bool use_tb = (d.sat_block == 0 || d.sat_block == 7) && transport_tb_supported(d);
+    bool use_cluster = !use_tb && d.sat_block != 1 && d.sat_block != 5 && d.sat_block != 6 && gc.nTiles <= 16;
     const int cluster_threads = half_tiles ? 512 : 1024;
     const size_t smem_cluster = ((size_t)2 * (gc.R + 2) * d.Ny + (size_t)gc.R * d.Ny) * sizeof(double);
     using cluster_fn = void (*)(Geo, Fluid, Wells, int, double, const int*, const double*, double*, const double*,
@@ -830,9 +799,33 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
         if (d.Ny == 128) cluster_kernel = d.por ? k_sat_cluster<true, 512, 2, 128> : k_sat_cluster<false, 512, 2, 128>;
         if (d.Ny == 64) cluster_kernel = d.por ? k_sat_cluster<true, 512, 2, 64> : k_sat_cluster<false, 512, 2, 64>;
     }
+    cudaLaunchConfig_t cluster_cfg{};
+    cudaLaunchAttribute cluster_attr[1];
     if (use_cluster) {
         HM_CUDA(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cluster));
         if (gc.nTiles > 8) HM_CUDA(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cluster_cfg.gridDim = dim3((unsigned)(nm * gc.nTiles));
+        cluster_cfg.blockDim = dim3(cluster_threads);
+        cluster_cfg.dynamicSmemBytes = smem_cluster;
+        cluster_cfg.stream = st;
+        cluster_attr[0].id = cudaLaunchAttributeClusterDimension;
+        cluster_attr[0].val.clusterDim.x = (unsigned)gc.nTiles;
+        cluster_attr[0].val.clusterDim.y = 1;
+        cluster_attr[0].val.clusterDim.z = 1;
+        cluster_cfg.attrs = cluster_attr;
+        cluster_cfg.numAttrs = 1;
+        // how many CTAs of this kernel the GPU holds at once (clusters must fit a GPC).  No resident cluster (a MIG
+        // slice, a part with fused-off SMs): the streaming kernel runs the same grid.
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, cluster_kernel, &cluster_cfg) != cudaSuccess) nc = 0;
+        (void)cudaGetLastError();
+        if (getenv("HM_DEBUG"))
+            fprintf(stderr, "[hm] k_sat_cluster: cluster of %d CTAs x %d threads, %zu B smem: max active clusters %d "
+                    "(%d CTAs on %d SMs)\n", gc.nTiles, cluster_threads, smem_cluster, nc, nc * gc.nTiles, ctx->sm_count);
+        if (nc > 0)
+            ctx->sim_stats.sat_resident_ctas = (int64_t)nc * gc.nTiles;
+        else
+            use_cluster = false;
     }
 
     // streaming transport (grids whose tiles do not fit a cluster, or sat_block 1): bulk-copy staged kernel when the
@@ -910,30 +903,14 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
 
         timer.mark(3);
         int sat_launches = 0;
-        if (use_cluster) {
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3((unsigned)(nm * gc.nTiles));
-            cfg.blockDim = dim3(cluster_threads);
-            cfg.dynamicSmemBytes = smem_cluster;
-            cfg.stream = st;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = (unsigned)gc.nTiles;
-            attr[0].val.clusterDim.y = 1;
-            attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
+        if (use_tb) {
+            double* Sres = nullptr;
+            HM_CHECK(transport_tb(ctx, d, fl, w, step, nm, max_nts, nts, Scur, Snxt, Vxl, Vyl, &Sres, &sat_launches));
+            if (Sres != Scur) std::swap(Scur, Snxt);
+        } else if (use_cluster) {
             const double* porp = d.por;
-            if (step == 0) {  // how many CTAs of this kernel the GPU holds at once (clusters must fit a GPC)
-                int nc = 0;
-                if (cudaOccupancyMaxActiveClusters(&nc, cluster_kernel, &cfg) == cudaSuccess)
-                    ctx->sim_stats.sat_resident_ctas = (int64_t)nc * gc.nTiles;
-                if (getenv("HM_DEBUG"))
-                    fprintf(stderr, "[hm] k_sat_cluster: cluster of %d CTAs x %d threads, %zu B smem: max active clusters %d "
-                            "(%d CTAs on %d SMs)\n", gc.nTiles, cluster_threads, smem_cluster, nc, nc * gc.nTiles, ctx->sm_count);
-            }
-            HM_CUDA(cudaLaunchKernelEx(&cfg, cluster_kernel, gc, fl, w, step, d.dt, (const int*)nts, (const double*)Scur,
-                                       Snxt, (const double*)Vxl, (const double*)Vyl, porp));
+            HM_CUDA(cudaLaunchKernelEx(&cluster_cfg, cluster_kernel, gc, fl, w, step, d.dt, (const int*)nts,
+                                       (const double*)Scur, Snxt, (const double*)Vxl, (const double*)Vyl, porp));
             std::swap(Scur, Snxt);
             sat_launches = 1;
         } else {

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import contextlib
 import multiprocessing
+from dataclasses import dataclass
 
 import numpy as np
 
@@ -20,35 +21,8 @@ from tools import utils
 _HALVINGS = tuple(0.5 ** (k + 1) for k in range(8))
 
 
-class _Record:
-    """Keyword-constructed record with positional order, repr and equality (what the notebooks rely on)."""
-
-    _fields: tuple = ()
-
-    def __init__(self, *args, **kwargs):
-        if len(args) > len(self._fields):
-            raise TypeError(f"{type(self).__name__} takes at most {len(self._fields)} positional arguments")
-        given = dict(zip((name for name, _ in self._fields), args))
-        clash = set(given) & set(kwargs)
-        if clash:
-            raise TypeError(f"{type(self).__name__} got multiple values for {sorted(clash)}")
-        given.update(kwargs)
-        unknown = set(given) - {name for name, _ in self._fields}
-        if unknown:
-            raise TypeError(f"{type(self).__name__} got unexpected arguments {sorted(unknown)}")
-        for name, default in self._fields:
-            setattr(self, name, given.get(name, default))
-
-    def __repr__(self):
-        body = ", ".join(f"{name}={getattr(self, name)!r}" for name, _ in self._fields)
-        return f"{type(self).__name__}({body})"
-
-    def __eq__(self, other):
-        return type(other) is type(self) and all(
-            np.array_equal(getattr(self, n), getattr(other, n)) for n, _ in self._fields)
-
-
-class nabla_ens(_Record):
+@dataclass
+class nabla_ens:
     """Gradient of ``obj`` at ``u`` estimated by linear regression on an ensemble of perturbed controls.
 
     ``chol``: Cholesky factor of the perturbation covariance (or a scalar standard deviation); ``nEns``: ensemble
@@ -57,7 +31,13 @@ class nabla_ens(_Record):
     the notebooks' robust-objective variants, which override ``ens_eval``.
     """
 
-    _fields = (("chol", 1.0), ("nEns", 10), ("precond", False), ("robustly", None), ("obj_ux", None), ("X", None))
+    # dataclass fields with class-level defaults, as in the reference (``nabla_ens.nEns``, ``dataclasses.replace`` work)
+    chol: float = 1.0
+    nEns: int = 10
+    precond: bool = False
+    robustly: None = None
+    obj_ux: None = None
+    X: None = None
 
     def ens_eval(self, obj, u, U, pbar):
         """Objective of every perturbed control: one batched forward run behind ``utils.apply``."""
@@ -82,7 +62,8 @@ def split(arr, step):
     return [arr[start:start + size] for start in range(0, len(arr), size)]
 
 
-class backtracker(_Record):
+@dataclass
+class backtracker:
     """Line search: try the step lengths ``xSteps`` in order, accept the first admissible improvement.
 
     ``sign`` = +1 maximises, -1 minimises; an improvement is admissible if it exceeds ``rtol * max(1e-8, |J0|)``.
@@ -90,7 +71,10 @@ class backtracker(_Record):
     Returns ``(u1, J1, info)`` or ``None`` when every trial is declined.
     """
 
-    _fields = (("sign", +1), ("xSteps", _HALVINGS), ("rtol", 1e-8), ("nCPU", None))
+    sign: int = +1
+    xSteps: tuple = _HALVINGS
+    rtol: float = 1e-8
+    nCPU: int = None
 
     def __call__(self, obj, u0, J0, search_direction, pbar):
         threshold = max(1e-8, abs(J0)) * self.rtol

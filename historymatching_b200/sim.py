@@ -58,10 +58,13 @@ _LANES: dict = {}  # (device, lane) -> (Context, torch stream): the extra lanes'
 
 
 def uses_cluster_transport(grid: GridSpec, sat_block=0) -> bool:
-    """Whether hm_sim_batch takes the streamed path with the cluster transport kernel for this grid (the tiling rule of
-    csrc/hm_sim.cu: row tiles of <= 2048 cells, even height, at most 16 tiles per member)."""
-    if sat_block in (1, 5) or (grid.M <= 2048 and sat_block == 0):
+    """Whether hm_sim_batch takes the streamed path with an on-chip transport kernel for this grid: the temporally blocked
+    kernel (csrc/hm_transport.cu: row length a multiple of 64) or the cluster kernel (the tiling rule of csrc/hm_sim.cu:
+    row tiles of <= 2048 cells, even height, at most 16 tiles per member)."""
+    if sat_block in (1, 5, 6) or (grid.M <= 2048 and sat_block == 0):
         return False
+    if sat_block in (0, 7) and grid.Ny % 64 == 0 and grid.Ny <= 2048:
+        return True
     R = max(1, min(grid.Nx, 2048 // grid.Ny))
     if 1 < R < grid.Nx:
         R &= ~1
@@ -140,7 +143,7 @@ def run_ensemble(grid: GridSpec, K, well_cell, well_rate, S0, dt, n_steps, *, n_
                 stats.setdefault(k, {})
                 for ph, ms in v.items():
                     stats[k][ph] = stats[k].get(ph, 0.0) + ms
-            elif k == "sat_resident_ctas":
+            elif k in ("sat_resident_ctas", "sat_tb_cluster", "sat_tb_strips", "sat_tb_halo"):
                 stats[k] = max(stats.get(k, 0), v)
             else:
                 stats[k] = stats.get(k, 0) + v
@@ -153,7 +156,7 @@ def _run_ensemble_one(grid: GridSpec, K, well_cell, well_rate, S0, dt, n_steps, 
                       _alloc_only=False,
                  obs_cell=None, por=None, history=False, pressure=False, want_substeps=False,
                  cg_rtol=0.0, cg_max_iter=0, chunk_members=0, precond=0, mg_switch_iters=0, sat_block=0, warm_start=0,
-                 ctx=None) -> SimResult:
+                 tb_cluster_rows=0, tb_halo=0, ctx=None) -> SimResult:
     """Run ``n_steps`` of the simulator for every ensemble member.
 
     K          (M,) shared isotropic; (N,M) isotropic; (N,2,M) anisotropic (Kx, Ky);
@@ -278,6 +281,7 @@ def _run_ensemble_one(grid: GridSpec, K, well_cell, well_rate, S0, dt, n_steps, 
     d.sat_block = int(sat_block)
     d.hist_stride = hist_stride
     d.warm_start = int(warm_start)
+    d.tb_cluster_rows, d.tb_halo = int(tb_cluster_rows), int(tb_halo)
 
     if use_torch:
         ctx = ctx or _lib.Context.get(dev.index if dev.index is not None else 0)
@@ -295,6 +299,8 @@ def _run_ensemble_one(grid: GridSpec, K, well_cell, well_rate, S0, dt, n_steps, 
         cg_iterations=st.cg_iterations, sat_substeps=st.sat_substeps,
         kernel_launches=st.kernel_launches, cg_kernel_launches=st.cg_kernel_launches,
         sat_kernel_launches=st.sat_kernel_launches, mg_fp64_fallbacks=st.mg_fp64_fallbacks, cg_restarts=st.cg_restarts, sat_resident_ctas=st.sat_resident_ctas,
+        sat_tb_cluster=st.sat_tb_cluster, sat_tb_strips=st.sat_tb_strips, sat_tb_halo=st.sat_tb_halo,
+        sat_cell_updates=st.sat_cell_updates,
         phase_ms=dict(zip(("setup", "cg", "flux", "saturation", "obs"), list(ph))),
     )
     return res

@@ -27,6 +27,20 @@ def notebook_wells(grid: GridSpec):
     return cells, rates
 
 
+def check_status(status):
+    """Warn about members whose forward run did not complete cleanly (``hm_sim_desc.status`` bits): a pressure solve that
+    hit the iteration limit, or a non-finite saturation.  The run is not aborted - an EnOpt batch may contain members
+    outside the admissible domain (``Optimise.py:548-555``) - but it must not pass silently."""
+    import warnings
+
+    bad = status.nonzero()
+    bad = bad[0] if isinstance(bad, tuple) else bad.reshape(-1)
+    if len(bad):
+        first = [int(i) for i in bad[:8]]
+        warnings.warn(f"forward run: {len(bad)} member(s) with a non-zero status (first: {first}); bit 1 = pressure solve "
+                      f"not converged, bit 2 = non-finite saturation", RuntimeWarning, stacklevel=3)
+
+
 class HistoryMatchCase:
     def __init__(self, Nx=20, Ny=20, Lx=2.0, Ly=1.0, dt=0.025, nTime=40, device=None):
         import scipy.linalg as sla
@@ -80,6 +94,7 @@ class HistoryMatchCase:
             wc, wr, oc = self.well_cell, self.well_rate, self.obs_cell
         res = run_ensemble(self.grid, K, wc, wr, S0, self.dt, self.nTime, obs_cell=oc, history=history,
                            n_members=K.shape[0], **kw)
+        check_status(res.status)
         return res.obs.reshape(K.shape[0], self.p), res
 
     def es_update(self, E, Eo, obs, Z, alpha=1.0):

@@ -116,12 +116,19 @@ typedef struct hm_sim_desc {
                             * The streaming kernel stages its tile with bulk copies (cp.async.bulk) when Ny is even.
                             * 4 = as 2 with tiles of 1024 cells, 512 threads, two CTAs per SM (measured: same speed).
                             * 5 = as 1 with the plain-load streaming kernel.  6 = as 1 with 2048-cell tiles (default: 4096
-                            * cells, 8 per thread, where the tile fits 110 KB of shared memory). */
+                            * cells, 8 per thread, where the tile fits 110 KB of shared memory).
+                            * Automatic choice on the streamed path: the temporally blocked kernel k_sat_tb (7) where the grid
+                            * qualifies (Ny a multiple of 64, no porosity field), else the cluster kernel (2) where a member's
+                            * tiles fit a cluster, else the streaming kernel (1).  7 = streamed path, k_sat_tb forced. */
     int32_t hist_stride;   /* <= 1: S_hist holds every step (the reference's ResSim.sim output); k > 1: every k-th step and
                             * the last one - the saturation history of a large ensemble for plotting / animation cells
                             * (HistoryMatch.py:233, 1212-1214) without n_steps+1 fields per member */
     int32_t warm_start;    /* initial guess of a pressure solve: 0 = linear extrapolation of the two previous pressures
                             * (default), 1 = the previous pressure (measured: same iteration counts) */
+    int32_t tb_cluster_rows; /* temporally blocked transport kernel (sat_block 0 / 7): tiles of a cluster along the grid rows;
+                            * <= 0: chosen from the grid and the device's cluster occupancy */
+    int32_t tb_halo;       /* the same kernel: sub-steps per round (= overlap rows of neighbouring row strips) when a member
+                            * does not fit one cluster; <= 0: automatic */
 } hm_sim_desc;
 
 /* statistics of the last hm_sim_batch on this ctx (host side) */
@@ -134,6 +141,10 @@ typedef struct hm_sim_stats {
     int64_t mg_fp64_fallbacks; /* pressure solves that switched from the FP32 to the FP64 multigrid cycle */
     int64_t cg_restarts;       /* long pressure solves continued after the check of the true residual */
     int64_t sat_resident_ctas; /* cluster transport kernel: CTAs the GPU holds at once (0: other transport path) */
+    int64_t sat_tb_cluster;    /* temporally blocked transport kernel: CTAs per cluster (0: other transport path), */
+    int64_t sat_tb_strips;     /* row strips per member (1: a cluster holds the whole member), */
+    int64_t sat_tb_halo;       /* sub-steps per round = overlap rows of neighbouring strips (0 with one strip) */
+    int64_t sat_cell_updates;  /* cell updates executed by the transport kernels, redundant halo-row updates included */
 } hm_sim_stats;
 
 /* All pointers in the descriptor are DEVICE pointers.  Synchronises the ctx

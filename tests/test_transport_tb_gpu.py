@@ -1,0 +1,210 @@
+"""GPU parity of the temporally blocked transport kernel k_sat_tb (csrc/hm_transport.cu) and of the BASELINE
+grid sizes (128^2, 512^2) against the CPU oracle.
+
+k_sat_tb is the default transport kernel of the streamed path wherever the row length is a multiple of 64
+(BASELINE configs C and D).  It is checked
+
+* against the oracle (saturations 1e-8, sub-step counts exactly), at 128 x 128 with the default kernels and at
+  512 x 512 (strips of a member advanced 16 sub-steps per launch);
+* against the cluster kernel k_sat_cluster / the streaming kernel k_sat_stream of round 1 (same face fluxes, a
+  different but equivalent summation order: agreement to rounding, 1e-12), over cluster shapes, ragged row counts
+  and forced strip / round geometries - including strips with overlap on both sides and a clipped last strip.
+"""
+
+import numpy as np
+import pytest
+
+from oracle import ressim as orr
+
+from test_sim_gpu import SAT_TOL, _oracle, _setup
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(grid, logk, cells, rates, nT, **kw):
+    from historymatching_b200.sim import run_ensemble
+
+    return run_ensemble(grid, orr.perm_transf(logk), cells, rates, np.zeros(grid.M), 0.025, nT, want_substeps=True, **kw)
+
+
+@pytest.mark.parametrize("Nx,Ny,N", [(128, 128, 3), (64, 64, 3), (96, 64, 2), (40, 256, 2), (72, 128, 2), (100, 128, 2),
+                                     (256, 256, 2), (33, 192, 2), (16, 1024, 1)])
+def test_tb_kernel_matches_round1_kernels(Nx, Ny, N):
+    """One cluster holds the whole member (all sub-steps of a time step in one launch).  One time step: the two kernels
+    see bit-identical fluxes and differ by the summation order only (1e-12); over two steps the second pressure solve
+    starts from saturations that differ in the last bits and is itself only accurate to the CG tolerance (1e-9)."""
+    m, grid, logk, cells, rates, prd = _setup(Nx, Ny, N, seed=Nx + Ny)
+    old = 2 if Nx * Ny <= 16 * 2048 else 1
+    for nT, tol in ((1, 1e-12), (2, 2e-9)):
+        ref = _run(grid, logk, cells, rates, nT, sat_block=old, obs_cell=prd)
+        new = _run(grid, logk, cells, rates, nT, sat_block=7, obs_cell=prd)
+        assert not new.status.any() and not ref.status.any()
+        assert new.stats["sat_tb_cluster"] >= 1 and new.stats["sat_tb_strips"] == 1
+        assert new.stats["sat_kernel_launches"] == nT
+        np.testing.assert_array_equal(new.substeps, ref.substeps)
+        np.testing.assert_allclose(new.S_last, ref.S_last, rtol=0, atol=tol)
+        np.testing.assert_allclose(new.obs, ref.obs, rtol=0, atol=tol)
+
+
+@pytest.mark.parametrize("Nx,Ny,rows,halo,strips", [
+    (128, 128, 1, 4, 5),     # 32-row strips, stride 24: starts 0,24,48,72,96
+    (128, 128, 2, 8, 3),     # 64-row strips, stride 48, the last one clipped to start 64
+    (128, 128, 2, 16, 3),
+    (256, 128, 4, 16, 3),    # 128-row strips of a 4-CTA cluster
+    (200, 256, 2, 8, 4),     # two tile columns (cy = 2): halo columns through DSMEM; ragged strip starts
+    (150, 64, 1, 8, 3),      # W = 64 tiles (64 rows each)
+])
+def test_tb_strips_match_streaming_kernel(Nx, Ny, rows, halo, strips):
+    """Temporal blocking across HBM: overlapping row strips, `halo` sub-steps per launch."""
+    m, grid, logk, cells, rates, prd = _setup(Nx, Ny, 2, seed=Nx + Ny + halo)
+    ref = _run(grid, logk, cells, rates, 1, sat_block=1, obs_cell=prd)
+    new = _run(grid, logk, cells, rates, 1, sat_block=7, tb_cluster_rows=rows, tb_halo=halo, obs_cell=prd)
+    assert not new.status.any()
+    assert new.stats["sat_tb_strips"] == strips and new.stats["sat_tb_halo"] == halo
+    nts = int(ref.substeps.max())
+    assert new.stats["sat_kernel_launches"] == -(-nts // halo)
+    np.testing.assert_array_equal(new.substeps, ref.substeps)
+    np.testing.assert_allclose(new.S_last, ref.S_last, rtol=0, atol=1e-12)
+    # a restart from a non-trivial state: every strip is wet, so a wrong halo row would show
+    S1 = new.S_last
+    from historymatching_b200.sim import run_ensemble
+
+    kw = dict(want_substeps=True, obs_cell=prd)
+    ref2 = run_ensemble(grid, orr.perm_transf(logk), cells, rates, np.sqrt(S1 + 0.05), 0.025, 1, sat_block=1, **kw)
+    new2 = run_ensemble(grid, orr.perm_transf(logk), cells, rates, np.sqrt(S1 + 0.05), 0.025, 1, sat_block=7,
+                        tb_cluster_rows=rows, tb_halo=halo, **kw)
+    np.testing.assert_array_equal(new2.substeps, ref2.substeps)
+    np.testing.assert_allclose(new2.S_last, ref2.S_last, rtol=0, atol=1e-12)
+
+
+def test_config_c_grid_matches_oracle():
+    """BASELINE config C grid (128 x 128) with the default kernels (FP32-cycle MG-PCG, k_sat_tb in a 4-CTA cluster):
+    saturations, observations, pressures and sub-step counts against the oracle."""
+    from historymatching_b200.sim import run_ensemble
+
+    m, grid, logk, cells, rates, prd = _setup(128, 128, 2, seed=7)
+    dt, nT = 0.025, 3
+    S0 = np.zeros(grid.M)
+    res = run_ensemble(grid, orr.perm_transf(logk), cells, rates, S0, dt, nT, obs_cell=prd, history=True, pressure=True,
+                       want_substeps=True)
+    assert not res.status.any()
+    assert res.stats["sat_tb_cluster"] == 4 and res.stats["sat_kernel_launches"] == nT
+    wsats, prods = _oracle(m, logk, dt, nT, S0, prd)
+    np.testing.assert_allclose(res.S_hist, wsats, rtol=0, atol=SAT_TOL)
+    np.testing.assert_allclose(res.obs, prods, rtol=0, atol=SAT_TOL)
+    for i in range(2):
+        mm = orr.notebook_model(128, 128)
+        p = orr.perm_transf(logk[i]).reshape(mm.shape)
+        mm.K = np.stack([p, p])
+        _, aux = mm.sim(dt, nT, S0, return_aux=True)
+        np.testing.assert_array_equal(res.substeps[i], aux["Nts"])
+        assert (res.substeps[i] == 615).all()
+        P = aux["P"][-1]
+        np.testing.assert_allclose(res.P_last[i], P, rtol=0, atol=1e-8 * np.abs(P).max())
+
+
+def test_config_c_grid_round1_cluster_kernel_matches_oracle():
+    """The same grid on the round-1 kernels (8-CTA k_sat_cluster<.,128>)."""
+    from historymatching_b200.sim import run_ensemble
+
+    m, grid, logk, cells, rates, prd = _setup(128, 128, 1, seed=8)
+    S0 = np.zeros(grid.M)
+    res = run_ensemble(grid, orr.perm_transf(logk), cells, rates, S0, 0.025, 2, obs_cell=prd, history=True, sat_block=2)
+    wsats, _ = _oracle(m, logk, 0.025, 2, S0, prd)
+    np.testing.assert_allclose(res.S_hist, wsats, rtol=0, atol=SAT_TOL)
+
+
+def test_config_d_grid_matches_oracle():
+    """BASELINE config D grid (512 x 512): one member, one time step = 9831 sub-steps, against the oracle (about a minute
+    of CPU).  Default kernels: three streamed multigrid levels, k_sat_tb on overlapping 128-row strips."""
+    from historymatching_b200.sim import run_ensemble
+
+    m, grid, logk, cells, rates, prd = _setup(512, 512, 1, seed=3)
+    dt = 0.025
+    S0 = np.zeros(grid.M)
+    res = run_ensemble(grid, orr.perm_transf(logk), cells, rates, S0, dt, 1, obs_cell=prd, pressure=True,
+                       want_substeps=True)
+    assert not res.status.any()
+    assert res.stats["sat_tb_strips"] > 1 and res.stats["sat_tb_halo"] >= 4
+    mm = orr.notebook_model(512, 512)
+    p = orr.perm_transf(logk[0]).reshape(mm.shape)
+    mm.K = np.stack([p, p])
+    ref, aux = mm.sim(dt, 1, S0, return_aux=True)
+    np.testing.assert_array_equal(res.substeps[0], aux["Nts"])
+    assert res.substeps[0, 0] == 9831
+    np.testing.assert_allclose(res.S_last[0], ref[-1], rtol=0, atol=SAT_TOL)
+    P = aux["P"][-1]
+    np.testing.assert_allclose(res.P_last[0], P, rtol=0, atol=1e-8 * np.abs(P).max())
+    # the round-1 streaming kernel on the same member
+    old = run_ensemble(grid, orr.perm_transf(logk), cells, rates, S0, dt, 1, sat_block=1)
+    np.testing.assert_allclose(old.S_last[0], ref[-1], rtol=0, atol=SAT_TOL)
+
+
+def test_tb_non_default_fluid_matches_oracle():
+    """Viscosity ratio and irreducible saturations (the non-unit fractional-flow instance of the kernel)."""
+    from historymatching_b200.sim import GridSpec, run_ensemble
+
+    m, grid, logk, cells, rates, prd = _setup(48, 64, 2, seed=19)
+    grid = GridSpec(48, 64, m.Lx, m.Ly, vw=0.8, vo=1.3, swc=0.1, sor=0.15)
+    S0 = np.full(grid.M, 0.1)
+    nT, dt = 4, 0.02
+    res = run_ensemble(grid, orr.perm_transf(logk), cells, rates, S0, dt, nT, obs_cell=prd, history=True,
+                       want_substeps=True, sat_block=7)
+    assert not res.status.any() and res.stats["sat_tb_cluster"] >= 1
+    for i in range(2):
+        om = orr.OracleResSim(48, 64, m.Lx, m.Ly, vw=0.8, vo=1.3, swc=0.1, sor=0.15)
+        p = orr.perm_transf(logk[i]).reshape(om.shape)
+        om.K = np.stack([p, p])
+        om.inj_xy, om.prd_xy, om.inj_rates, om.prd_rates = m.inj_xy, m.prd_xy, m.inj_rates, m.prd_rates
+        ref, aux = om.sim(dt, nT, S0, return_aux=True)
+        np.testing.assert_array_equal(res.substeps[i], aux["Nts"])
+        np.testing.assert_allclose(res.S_hist[i], ref, rtol=0, atol=SAT_TOL)
+
+
+def test_tb_per_member_wells_anywhere_in_the_tile():
+    """EnOpt-style batches: wells differ per member; several wells inside one thread's 4 x 2 patch, wells on tile and
+    cluster edges, two wells in one cell, time-dependent rates."""
+    from historymatching_b200.sim import GridSpec, run_ensemble
+
+    Nx, Ny, nT, dt = 64, 128, 3, 0.02
+    grid = GridSpec(Nx=Nx, Ny=Ny, Lx=2.0, Ly=1.0)
+    rng = np.random.RandomState(12)
+    K = np.exp(rng.randn(Nx * Ny) * 0.4)
+    N = 4
+    special = [
+        [(0, 0), (1, 1), (3, 0), (31, 127), (32, 0)],      # three wells in the patch of thread 0, both sides of a tile edge
+        [(63, 127), (63, 126), (60, 127), (32, 64), (31, 64)],
+        [(10, 10), (10, 10), (40, 100), (41, 101), (5, 64)],  # two wells in one cell
+        [tuple(rng.randint(0, [Nx, Ny])) for _ in range(5)],
+    ]
+    wc = np.zeros((N, 5), np.int32)
+    wr = np.zeros((N, nT, 5))
+    S_ref = []
+    for i in range(N):
+        m = orr.OracleResSim(Nx, Ny, 2.0, 1.0)
+        m.K = np.stack([K.reshape(Nx, Ny)] * 2)
+        idx = np.array([ix * Ny + iy for ix, iy in special[i]])
+        m.inj_xy = m.ind2xy(idx[:2]).T
+        m.prd_xy = m.ind2xy(idx[2:]).T
+        inj = 0.3 + rng.rand(2, nT)
+        w = rng.rand(3, nT)
+        w /= w.sum(0)
+        m.inj_rates = inj
+        m.prd_rates = w * inj.sum(0)
+        wc[i] = np.concatenate([m.xy2ind(*m.inj_xy.T), m.xy2ind(*m.prd_xy.T)])
+        assert (wc[i] == idx).all()
+        wr[i] = np.concatenate([m.inj_rates, -m.prd_rates]).T
+        S_ref.append(m.sim(dt, nT, np.zeros(Nx * Ny)))
+    res = run_ensemble(grid, K, wc, wr, np.zeros(Nx * Ny), dt, nT, history=True, n_members=N, sat_block=7)
+    assert not res.status.any() and res.stats["sat_tb_cluster"] == 2
+    np.testing.assert_allclose(res.S_hist, np.array(S_ref), rtol=0, atol=SAT_TOL)
+
+
+def test_porosity_field_takes_the_round1_kernels():
+    """k_sat_tb assumes a uniform pore volume; with a porosity field the automatic choice is the cluster kernel."""
+    from historymatching_b200.sim import run_ensemble
+
+    m, grid, logk, cells, rates, prd = _setup(64, 64, 1, seed=2)
+    por = 0.5 + 0.5 * np.random.RandomState(0).rand(grid.M)
+    res = run_ensemble(grid, orr.perm_transf(logk), cells, rates, np.zeros(grid.M), 0.025, 1, por=por)
+    assert res.stats["sat_tb_cluster"] == 0 and res.stats["sat_resident_ctas"] > 0
