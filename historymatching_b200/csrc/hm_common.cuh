@@ -102,6 +102,6 @@ struct hm_ctx {
     hm_sim_stats sim_stats{};
     int64_t launches = 0;  // kernels of this library launched on the ctx
     double phase_ms[5] = {0, 0, 0, 0, 0};
-    int tb_active[2][2][17] = {};  // k_sat_tb<W, UNIT>: resident clusters per cluster size (0 = not queried, -1 = none)
+    int tb_active[4][2][17] = {};  // k_sat_tb<W, UNIT>: resident clusters per cluster size (0 = not queried, -1 = none)
     bool mg_force64 = false;  // pressure_solve: the FP32 multigrid cycle converged too slowly in this forward run
 };

@@ -36,6 +36,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// asynchronous 4 / 8 byte copies global -> shared (LDGSTS); completion: cp.async.wait_all of the issuing thread
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+
 // predicated form: no branch (and no convergence barrier) around the store in the sub-step loop
 __device__ __forceinline__ void st_async_f64_if(bool pred, uint32_t remote_addr, double v, uint32_t remote_bar) {
     asm volatile(

@@ -29,6 +29,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "hm_ptx.cuh"
@@ -49,6 +50,7 @@ struct TbArgs {
     double h2;      // hx * hy
     int step;       // time step (well rate schedule)
     int it0, kmax;  // this launch advances sub-steps it0 .. it0 + kmax - 1 (clipped to the member's count)
+    int nWork;      // work items (member, strip) of the launch, dealt round-robin to the persistent clusters
     double dt;
     const int* nts;
     const double* Sin;
@@ -65,108 +67,59 @@ __device__ __forceinline__ double upwind(double w, double f_lo, double f_hi) {
     return __double2hiint(w) > 0 ? f_lo : f_hi;
 }
 
+template <int W>
+struct TbLayout {
+    static constexpr int H = W / 2;            // threads per row group (each owns 2 columns)
+    static constexpr int R = kTbCells / W;     // rows of the CTA tile
+    static constexpr int RSD = W + 2;          // doubles per published row: E[0..H] (E[H] = right halo), O[-1..H-1] (O[-1] = left halo)
+    static constexpr int NQ = R / 4;           // row groups
+    static constexpr int BUF = (R + 2) * RSD;  // one fw buffer: halo row, R tile rows, halo row
+    static constexpr int OO = H + 2;           // offset of O[c] behind E[c] in a row
+    // staging of the NEXT work item (bulk copies, one mbarrier): S rows, x-flux rows (one more), y-flux rows (two more columns)
+    static constexpr int ST_S = 2 * BUF, ST_X = ST_S + R * W, ST_Y = ST_X + (R + 1) * W, TOTAL = ST_Y + R * (W + 2);
+};
+
 template <int W, bool UNIT>
 __global__ void __launch_bounds__(kTbThreads, 1) k_sat_tb(TbArgs a, Fluid fl, Wells w) {
     namespace cg = cooperative_groups;
-    constexpr int H = W / 2;            // threads per row group (each owns 2 columns)
-    constexpr int R = kTbCells / W;     // rows of the CTA tile
-    constexpr int RSD = W + 2;          // doubles per published row: E[0..H] (E[H] = right halo), O[-1..H-1] (O[-1] = left halo)
-    constexpr int NQ = R / 4;           // row groups
-    constexpr int BUF = (R + 2) * RSD;  // one fw buffer: halo row, R tile rows, halo row
-    constexpr int OO = H + 2;           // offset of O[c] behind E[c] in a row
-    extern __shared__ __align__(16) double smt[];  // fw[2][BUF]
-    __shared__ int wc[kMaxWells];
-    __shared__ double wr[kMaxWells];
+    using L = TbLayout<W>;
+    constexpr int H = L::H, R = L::R, RSD = L::RSD, NQ = L::NQ, BUF = L::BUF, OO = L::OO;
+    extern __shared__ __align__(16) double smt[];  // fw[2][BUF], staging
+    __shared__ int wcs[2][kMaxWells];  // wells and sub-step count of this and of the next work item (cp.async)
+    __shared__ double wrs[2][kMaxWells];
+    __shared__ int ntss[2];
     __shared__ int wl_tid[kMaxWells], wl_slot[kMaxWells];
     __shared__ double wl_neg[kMaxWells], wl_pos[kMaxWells];
     __shared__ int wl_n;
-    __shared__ __align__(8) unsigned long long bars[2];
+    __shared__ __align__(8) unsigned long long bars[4];  // halo exchange (per fw buffer), staging, CTA split barrier
 
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = a.cx * a.cy;
     const int rank = (int)cluster.block_rank();
-    const int work = blockIdx.x / csize;
-    const int m = work / a.nStrips, sidx = work - m * a.nStrips;
     const int cxi = rank / a.cy, cyi = rank - cxi * a.cy;
     const int sMax = max(a.Nx - a.cx * R, 0);
-    const int s0 = min(sidx * a.stride, sMax);  // first grid row of the strip
-    const int vlo = sidx == 0 ? 0 : s0 + a.halo;  // rows [vlo, vhi) are exact after the round and written back
-    const int vhi = sidx == a.nStrips - 1 ? a.Nx : min((sidx + 1) * a.stride, sMax) + a.halo;
     const int tid = threadIdx.x, q = tid / H, c = tid - q * H;
-    const int row0 = s0 + cxi * R + 4 * q;  // first grid row of the thread's patch
-    const int col = cyi * W + 2 * c;        // first grid column of the patch
-    const int n = a.nts[m];
-    const int nr = max(0, min(a.kmax, n - a.it0));  // sub-steps of this launch
-    const double dts = n > 0 ? a.dt / (double)n : 0.0;
-    const double dtx = dts / a.h2;
-    const int64_t mb = (int64_t)m * a.M;
+    const int col0 = cyi * W;
+    // Persistent clusters: cluster k advances the work items (member, strip) k, k + nClusters, ... of this round.
+    const int nClusters = gridDim.x / csize, nWork = a.nWork;
+    int work = blockIdx.x / csize;
 
     for (int e = tid; e < 2 * BUF; e += kTbThreads) smt[e] = 0.0;  // halo slots without a neighbour stay zero
-    if (tid == 0) wl_n = 0;
-    load_wells(w, m, a.step, wc, wr);
-    __syncthreads();
-    // wells of this tile: (owning thread, cell slot in its patch, dtx * min(q,0), dtx * max(q,0))
-    for (int i = tid; i < w.n; i += kTbThreads) {
-        const int cc = wc[i];
-        bool first = true;
-        for (int k = 0; k < i; ++k) first = first && (wc[k] != cc);
-        if (!first) continue;
-        const int gr = cc / a.Ny, gc = cc - gr * a.Ny;
-        const int lr = gr - (s0 + cxi * R), lc = gc - cyi * W;
-        if (lr < 0 || lr >= R || lc < 0 || lc >= W) continue;
-        const double qs = cell_source(cc, w.n, wc, wr) * dtx;
-        const int e = atomicAdd(&wl_n, 1);
-        wl_tid[e] = (lr >> 2) * H + (lc >> 1);
-        wl_slot[e] = (lr & 3) * 2 + (lc & 1);
-        wl_neg[e] = fmin(qs, 0.0);
-        wl_pos[e] = fmax(qs, 0.0);
-    }
-    __syncthreads();
-    const int nwl = wl_n;
-    int we0 = -1;  // this thread's first entry of the list (-1: its patch holds no well)
-    for (int e = nwl - 1; e >= 0; --e)
-        if (wl_tid[e] == tid) we0 = e;
-    if (a.probe & 2) we0 = -1;
-
-    // state of the patch: saturations and signed face coefficients dtx * v.  wx[r][j]: face between rows r-1 and r
-    // of the patch (r = 0..4), wy[r][j]: face between columns j-1 and j (j = 0..2).  Rows beyond the grid (ragged
-    // last tile of a single-strip member) hold S = 0 and zero coefficients: inert.
-    double S[4][2], wx[5][2], wy[4][3];
-#pragma unroll
-    for (int r = 0; r < 5; ++r) {
-        const int gr = row0 + r;
-        wx[r][0] = wx[r][1] = 0.0;
-        if (gr < a.Nx) {
-            const double2 v = *reinterpret_cast<const double2*>(a.Vxl + mb + (int64_t)gr * a.Ny + col);
-            wx[r][0] = dtx * v.x;
-            wx[r][1] = dtx * v.y;
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int gr = row0 + r;
-        S[r][0] = S[r][1] = 0.0;
-        wy[r][0] = wy[r][1] = wy[r][2] = 0.0;
-        if (gr < a.Nx) {
-            const int64_t gi = mb + (int64_t)gr * a.Ny + col;
-            const double2 s = *reinterpret_cast<const double2*>(a.Sin + gi);
-            const double2 v = *reinterpret_cast<const double2*>(a.Vyl + gi);
-            S[r][0] = s.x;
-            S[r][1] = s.y;
-            wy[r][0] = dtx * v.x;
-            wy[r][1] = dtx * v.y;
-            wy[r][2] = dtx * a.Vyl[gi + 2];  // column Ny is column 0 of the next row: a zero face
-        }
-    }
+    double* const stS = smt + L::ST_S;
+    double* const stX = smt + L::ST_X;
+    double* const stY = smt + L::ST_Y;
 
     // halo exchange: this thread's one row neighbour (up or down) and one column neighbour (left or right)
-    const uint32_t bar0 = smem_u32(&bars[0]), bar1 = smem_u32(&bars[1]);
+    const uint32_t bar0 = smem_u32(&bars[0]), bar1 = smem_u32(&bars[1]), ldbar = smem_u32(&bars[2]), ctabar = smem_u32(&bars[3]);
+    int cpar = 0;
     const bool hx_ = !(a.probe & 1);
     const bool hasUp = hx_ && cxi > 0, hasDn = hx_ && cxi < a.cx - 1, hasLf = hx_ && cyi > 0, hasRt = hx_ && cyi < a.cy - 1;
     const int haloBytes = 8 * (W * ((int)hasUp + (int)hasDn) + R * ((int)hasLf + (int)hasRt));
     if (tid == 0) {
         mbar_init(bar0, 1);
         mbar_init(bar1, 1);
+        mbar_init(ldbar, 1);
+        mbar_init(ctabar, kTbThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (haloBytes) {  // first expectation of either barrier, re-posted in the loop by a waiter
             mbar_expect_tx(bar0, haloBytes);
@@ -190,11 +143,57 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_sat_tb(TbArgs a, Fluid fl, We
     const uint32_t xb0 = map_to_cta(bar0, xrank), xb1 = map_to_cta(bar1, xrank);
     const uint32_t ya0 = map_to_cta(smem_u32(fb0 + yoff), yrank), ya1 = map_to_cta(smem_u32(fb1 + yoff), yrank);
     const uint32_t yb0 = map_to_cta(bar0, yrank), yb1 = map_to_cta(bar1, yrank);
+
+    // A work item's tile into the staging buffers: bulk copies issued by warp 0, completion on ldbar.  A tile of whole grid
+    // rows (cy == 1) is contiguous in memory: three copies; otherwise one copy per tile row and array.  Rows beyond the
+    // grid (ragged last tile of a single-strip member) are not copied and read as zero below.  The item's wells and its
+    // sub-step count follow with cp.async (completion: cp.async.wait_all of the issuing threads + the next CTA barrier).
+    const int ysd = a.cy == 1 ? W : W + 2;  // row pitch of the staged y-fluxes
+    auto prefetch = [&](int wk, int slot) {
+        const int pm = wk / a.nStrips, ps = wk - pm * a.nStrips;
+        if (tid < 32) {
+            const int tr0 = min(ps * a.stride, sMax) + cxi * R;
+            const int rowsS = max(0, min(R, a.Nx - tr0)), rowsX = max(0, min(R + 1, a.Nx - tr0));
+            const int64_t g0 = (int64_t)pm * a.M + (int64_t)tr0 * a.Ny + col0;
+            if (a.cy == 1) {
+                if (tid == 0) {
+                    const uint32_t bS = 8u * rowsS * W, bX = 8u * rowsX * W, bY = rowsS ? bS + 16u : 0u;
+                    mbar_expect_tx(ldbar, (int)(bS + bX + bY));
+                    if (bS) bulk_g2s(smem_u32(stS), a.Sin + g0, bS, ldbar);
+                    if (bX) bulk_g2s(smem_u32(stX), a.Vxl + g0, bX, ldbar);
+                    if (bY) bulk_g2s(smem_u32(stY), a.Vyl + g0, bY, ldbar);
+                }
+            } else {
+                if (tid == 0) mbar_expect_tx(ldbar, 8 * (rowsS * W + rowsX * W + rowsS * (W + 2)));
+                __syncwarp();
+                for (int r = tid; r < rowsS; r += 32) bulk_g2s(smem_u32(stS + r * W), a.Sin + g0 + (int64_t)r * a.Ny, 8u * W, ldbar);
+                for (int r = tid; r < rowsX; r += 32) bulk_g2s(smem_u32(stX + r * W), a.Vxl + g0 + (int64_t)r * a.Ny, 8u * W, ldbar);
+                for (int r = tid; r < rowsS; r += 32)
+                    bulk_g2s(smem_u32(stY + r * (W + 2)), a.Vyl + g0 + (int64_t)r * a.Ny, 8u * (W + 2), ldbar);
+            }
+        } else if (tid < 32 + w.n) {
+            const int i = tid - 32;
+            cp_async_4(smem_u32(&wcs[slot][i]), w.cell + (int64_t)pm * w.cell_ms + i);
+            cp_async_8(smem_u32(&wrs[slot][i]), w.rate + (int64_t)pm * w.rate_ms + (int64_t)a.step * w.rate_ss + i);
+        } else if (tid == 32 + kMaxWells) {
+            cp_async_4(smem_u32(&ntss[slot]), a.nts + pm);
+        }
+    };
+    __syncthreads();  // ldbar initialised before warp 0 uses it
+    if (work < nWork) prefetch(work, 0);
     cluster.sync();  // tiles zeroed and mbarriers initialised in every CTA before remote traffic starts
+
+    // state of the patch: saturations and signed face coefficients dtx * v.  wx[r][j]: face between rows r-1 and r
+    // of the patch (r = 0..4), wy[r][j]: face between columns j-1 and j (j = 0..2).
+    double S[4][2], wx[5][2], wy[4][3];
+    int wcode = -1, nwl = 0;
 
     // Hazards (as in k_sat_cluster): the threads that read a halo row / column filled by a neighbour are exactly the
     // threads that send the matching edge row / column to that neighbour, and a sender has waited for the complete
-    // previous phase, so no neighbour runs more than one sub-step ahead of a reader; tiles and halos are double buffered.
+    // previous phase, so no neighbour runs more than one sub-step ahead of a reader; tiles and halos are double
+    // buffered.  The sub-step counter (buffer and mbarrier phase) runs on across the work items of a cluster, whose CTAs
+    // all execute the same sequence of sub-steps, so no cluster barrier is needed between items or at the end: a CTA
+    // has received everything its neighbours send before it leaves its last sub-step.
     auto substep = [&](double* __restrict__ fw, uint32_t mybar, uint32_t xa, uint32_t xb, uint32_t ya, uint32_t yb,
                        int parity) {
         double f[4][2];
@@ -202,9 +201,16 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_sat_tb(TbArgs a, Fluid fl, We
         for (int r = 0; r < 4; ++r) {
             f[r][0] = frac_flow_loop<UNIT>(S[r][0], fl);
             f[r][1] = frac_flow_loop<UNIT>(S[r][1], fl);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
             fw[r * RSD] = f[r][0];
             fw[r * RSD + OO] = f[r][1];
         }
+        // Split CTA barrier (an mbarrier counting all threads): arrive as soon as this thread's fw values are published, wait
+        // only where the neighbours' values are needed - the halo sends, the faces inside the patch and the well terms of
+        // a warp overlap with the other warps' publishing (measured at 128^2: 18.2 -> 16.2 ms per launch against bar.sync)
+        if (!(a.probe & 4)) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ctabar) : "memory");
         // edge rows / columns into the neighbours' halo slots.  (STAS cannot be predicated: one branch per direction,
         // the row direction is warp-uniform, the column direction is taken by one lane per warp.)
         if (sX) {
@@ -230,72 +236,217 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_sat_tb(TbArgs a, Fluid fl, We
             S[r][0] = fma(-wy[r][1], fu, S[r][0]);
             S[r][1] = fma(wy[r][1], fu, S[r][1]);
         }
-        if (we0 >= 0) {  // S += dtx * (min(q,0) fw(S) + max(q,0)) on the cells that hold wells
-            for (int e = we0; e < nwl; ++e) {
-                if (wl_tid[e] != tid) continue;
-                const int sl = wl_slot[e];
-                const double qn = wl_neg[e], qp = wl_pos[e];
+        if (wcode >= 0) {  // S += dtx * (min(q,0) fw(S) + max(q,0)) on the cells that hold wells: one lane of one warp
+            const int we0 = wcode & 255;
+            const double qn = wl_neg[we0], qp = wl_pos[we0];
+            switch ((wcode >> 8) & 255) {  // the slot is fixed for the work item: a jump table, then two FP64 operations
+                case 0: S[0][0] += fma(qn, f[0][0], qp); break;
+                case 1: S[0][1] += fma(qn, f[0][1], qp); break;
+                case 2: S[1][0] += fma(qn, f[1][0], qp); break;
+                case 3: S[1][1] += fma(qn, f[1][1], qp); break;
+                case 4: S[2][0] += fma(qn, f[2][0], qp); break;
+                case 5: S[2][1] += fma(qn, f[2][1], qp); break;
+                case 6: S[3][0] += fma(qn, f[3][0], qp); break;
+                default: S[3][1] += fma(qn, f[3][1], qp); break;
+            }
+            if (wcode >> 16) {  // further wells in the same 4 x 2 patch (rare)
+                for (int e = we0 + 1; e < nwl; ++e) {
+                    if (wl_tid[e] != tid) continue;
+                    const int sl = wl_slot[e];
+                    const double qn2 = wl_neg[e], qp2 = wl_pos[e];
 #pragma unroll
-                for (int r = 0; r < 4; ++r)
+                    for (int r = 0; r < 4; ++r)
 #pragma unroll
-                    for (int j = 0; j < 2; ++j)
-                        if (sl == 2 * r + j) S[r][j] += fma(qn, f[r][j], qp);
+                        for (int j = 0; j < 2; ++j)
+                            if (sl == 2 * r + j) S[r][j] += fma(qn2, f[r][j], qp2);
+                }
             }
         }
-        if (!(a.probe & 4)) __syncthreads();
-        if (needWait) {
-            mbar_wait(mybar, parity);
-            if (poster) mbar_expect_tx(mybar, haloBytes);
+        if (!(a.probe & 4)) {
+            mbar_wait(ctabar, cpar);
+            cpar ^= 1;
         }
         // the 12 faces on the boundary of the patch
+        auto halo_wait = [&]() {
+            mbar_wait(mybar, parity);
+            if (poster) mbar_expect_tx(mybar, haloBytes);
+        };
+        auto top = [&]() {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const double fn = fw[-RSD + j * OO];
-            S[0][j] = fma(wx[0][j], upwind(wx[0][j], fn, f[0][j]), S[0][j]);
-            const double fs = fw[4 * RSD + j * OO];
-            S[3][j] = fma(-wx[4][j], upwind(wx[4][j], f[3][j], fs), S[3][j]);
-        }
+            for (int j = 0; j < 2; ++j) {
+                const double fn = fw[-RSD + j * OO];
+                S[0][j] = fma(wx[0][j], upwind(wx[0][j], fn, f[0][j]), S[0][j]);
+            }
+        };
+        auto bottom = [&]() {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const double fl_ = fw[r * RSD + OO - 1];  // O[c-1]: column 2c-1
-            S[r][0] = fma(wy[r][0], upwind(wy[r][0], fl_, f[r][0]), S[r][0]);
-            const double fr_ = fw[r * RSD + 1];  // E[c+1]: column 2c+2
-            S[r][1] = fma(-wy[r][2], upwind(wy[r][2], f[r][1], fr_), S[r][1]);
-        }
+            for (int j = 0; j < 2; ++j) {
+                const double fs = fw[4 * RSD + j * OO];
+                S[3][j] = fma(-wx[4][j], upwind(wx[4][j], f[3][j], fs), S[3][j]);
+            }
+        };
+        auto sides = [&]() {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const double fl_ = fw[r * RSD + OO - 1];  // O[c-1]: column 2c-1
+                S[r][0] = fma(wy[r][0], upwind(wy[r][0], fl_, f[r][0]), S[r][0]);
+                const double fr_ = fw[r * RSD + 1];  // E[c+1]: column 2c+2
+                S[r][1] = fma(-wy[r][2], upwind(wy[r][2], f[r][1], fr_), S[r][1]);
+            }
+        };
+        if (needWait) halo_wait();
+        top();
+        bottom();
+        sides();
     };
     double* const fwa = fb0 + tb;
     double* const fwb = fb1 + tb;
-    int sub = 0;
-    for (; sub + 1 < nr; sub += 2) {
-        const int par = (sub >> 1) & 1;
-        substep(fwa, bar0, xa0, xb0, ya0, yb0, par);
-        substep(fwb, bar1, xa1, xb1, ya1, yb1, par);
-    }
-    if (sub < nr) substep(fwa, bar0, xa0, xb0, ya0, yb0, (sub >> 1) & 1);
+    __shared__ long long tstamp[8][6];
+    const bool trace = (a.probe & 32) && blockIdx.x < csize && a.it0 == a.kmax && tid == 0;
+    auto stamp = [&](int item, int k) {
+        if (trace && item < 8) {
+            long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            tstamp[item][k] = t;
+        }
+    };
+    int gsub = 0;  // sub-steps executed by this cluster so far: buffer = gsub & 1, mbarrier phase = (gsub >> 1) & 1
 
+    for (int item = 0; work < nWork; work += nClusters, ++item) {
+        const int m = work / a.nStrips, sidx = work - m * a.nStrips;
+        const int s0 = min(sidx * a.stride, sMax);      // first grid row of the strip
+        const int vlo = sidx == 0 ? 0 : s0 + a.halo;    // rows [vlo, vhi) are exact after the round and written back
+        const int vhi = sidx == a.nStrips - 1 ? a.Nx : min((sidx + 1) * a.stride, sMax) + a.halo;
+        const int row0 = s0 + cxi * R + 4 * q;          // first grid row of the thread's patch
+        const int slot = item & 1;
+
+        // staged tile -> registers.  Rows beyond the grid hold S = 0 and zero coefficients: inert.
+        stamp(item, 0);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();  // this item's wells and sub-step count (cp.async of other threads) are visible
+        const int n = ntss[slot];
+        const int nr = max(0, min(a.kmax, n - a.it0));  // sub-steps of this launch
+        const double dts = n > 0 ? a.dt / (double)n : 0.0;
+        const double dtx = dts / a.h2;
+        const int* wc = wcs[slot];
+        const double* wr = wrs[slot];
+        mbar_wait(ldbar, item & 1);
+        stamp(item, 1);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int gr = row0 + r;
-        if (gr >= vlo && gr < vhi)
-            *reinterpret_cast<double2*>(a.Sout + mb + (int64_t)gr * a.Ny + col) = make_double2(S[r][0], S[r][1]);
+        for (int r = 0; r < 5; ++r) {
+            wx[r][0] = wx[r][1] = 0.0;
+            if (row0 + r < a.Nx) {
+                const double2 v = *reinterpret_cast<const double2*>(stX + (4 * q + r) * W + 2 * c);
+                wx[r][0] = dtx * v.x;
+                wx[r][1] = dtx * v.y;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            S[r][0] = S[r][1] = 0.0;
+            wy[r][0] = wy[r][1] = wy[r][2] = 0.0;
+            if (row0 + r < a.Nx) {
+                const double2 sv = *reinterpret_cast<const double2*>(stS + (4 * q + r) * W + 2 * c);
+                const double* yp = stY + (4 * q + r) * ysd + 2 * c;
+                const double2 v = *reinterpret_cast<const double2*>(yp);
+                S[r][0] = sv.x;
+                S[r][1] = sv.y;
+                wy[r][0] = dtx * v.x;
+                wy[r][1] = dtx * v.y;
+                wy[r][2] = dtx * yp[2];  // column Ny is column 0 of the next row: a zero face
+            }
+        }
+        if (tid == 0) wl_n = 0;
+        __syncthreads();  // the staging buffers are free, the well list of the previous item is no longer read
+        if (work + nClusters < nWork) prefetch(work + nClusters, slot ^ 1);  // overlaps this item's sub-steps
+        // wells of this tile: (owning thread, cell slot in its patch, dtx * min(q,0), dtx * max(q,0))
+        for (int i = tid; i < w.n; i += kTbThreads) {
+            const int cc = wc[i];
+            bool first = true;
+            for (int k = 0; k < i; ++k) first = first && (wc[k] != cc);
+            if (!first) continue;
+            const int gr = cc / a.Ny, gc = cc - gr * a.Ny;
+            const int lr = gr - (s0 + cxi * R), lc = gc - col0;
+            if (lr < 0 || lr >= R || lc < 0 || lc >= W) continue;
+            const double qs = cell_source(cc, w.n, wc, wr) * dtx;
+            const int e = atomicAdd(&wl_n, 1);
+            wl_tid[e] = (lr >> 2) * H + (lc >> 1);
+            wl_slot[e] = (lr & 3) * 2 + (lc & 1);
+            wl_neg[e] = fmin(qs, 0.0);
+            wl_pos[e] = fmax(qs, 0.0);
+        }
+        __syncthreads();
+        nwl = wl_n;
+        // this thread's first entry of the list, its cell slot and "the patch holds further wells", packed into one
+        // register (-1: the patch holds no well)
+        wcode = -1;
+        for (int e = nwl - 1; e >= 0; --e)
+            if (wl_tid[e] == tid) wcode = e | (wl_slot[e] << 8) | (wcode >= 0 ? 1 << 16 : 0);
+        if (a.probe & 2) wcode = -1;
+        stamp(item, 2);
+
+        int sub = 0;
+        if ((gsub & 1) && nr > 0) {  // an odd number of sub-steps so far: the next one uses the second buffer
+            substep(fwb, bar1, xa1, xb1, ya1, yb1, (gsub >> 1) & 1);
+            ++sub, ++gsub;
+        }
+        for (; sub + 1 < nr; sub += 2, gsub += 2) {
+            const int par = (gsub >> 1) & 1;
+            substep(fwa, bar0, xa0, xb0, ya0, yb0, par);
+            substep(fwb, bar1, xa1, xb1, ya1, yb1, par);
+        }
+        if (sub < nr) {
+            substep(fwa, bar0, xa0, xb0, ya0, yb0, (gsub >> 1) & 1);
+            ++gsub;
+        }
+        stamp(item, 3);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int gr = row0 + r;
+            if (gr >= vlo && gr < vhi)
+                *reinterpret_cast<double2*>(a.Sout + (int64_t)m * a.M + (int64_t)gr * a.Ny + col0 + 2 * c) =
+                    make_double2(S[r][0], S[r][1]);
+        }
+        stamp(item, 4);
     }
-    cluster.sync();  // no CTA may exit while a neighbour can still write into its shared memory
+    if (trace) {
+        for (int i = 0; i < 6; ++i)
+            printf("[tb trace] cta %2d item %d: wait-load %6lld  setup %6lld  loop %6lld  store %6lld | item start +%lld ns\n", rank, i,
+                   tstamp[i][1] - tstamp[i][0], tstamp[i][2] - tstamp[i][1], tstamp[i][3] - tstamp[i][2],
+                   tstamp[i][4] - tstamp[i][3], tstamp[i][0] - tstamp[0][0]);
+    }
 }
 
 using tb_fn = void (*)(TbArgs, Fluid, Wells);
 
-static tb_fn tb_kernel(int W, bool unit) {
-    if (W == 128) return unit ? k_sat_tb<128, true> : k_sat_tb<128, false>;
-    return unit ? k_sat_tb<64, true> : k_sat_tb<64, false>;
+// Tile width: the largest of 512 / 256 / 128 / 64 that divides the row length.  A tile of whole grid rows (W == Ny) has no
+// column neighbours: its halo exchange is whole warps sending whole rows, and its staging copies are contiguous.
+static int tb_tile_cols(int Ny) {
+    if (getenv("HM_TB_W") && Ny % atoi(getenv("HM_TB_W")) == 0) return atoi(getenv("HM_TB_W"));  // development
+    for (int W : {512, 256, 128, 64})
+        if (Ny % W == 0) return W;
+    return 0;
 }
 
-static size_t tb_smem(int W) { return (size_t)2 * (kTbCells / W + 2) * (W + 2) * sizeof(double); }
+static tb_fn tb_kernel(int W, bool unit) {
+    switch (W) {
+        case 512: return unit ? k_sat_tb<512, true> : k_sat_tb<512, false>;
+        case 256: return unit ? k_sat_tb<256, true> : k_sat_tb<256, false>;
+        case 128: return unit ? k_sat_tb<128, true> : k_sat_tb<128, false>;
+        default: return unit ? k_sat_tb<64, true> : k_sat_tb<64, false>;
+    }
+}
+
+static size_t tb_smem(int W) {
+    const int n = W == 512 ? TbLayout<512>::TOTAL : W == 256 ? TbLayout<256>::TOTAL : W == 128 ? TbLayout<128>::TOTAL
+                                                                                                  : TbLayout<64>::TOTAL;
+    return (size_t)n * sizeof(double);
+}
 
 bool transport_tb_supported(const hm_sim_desc& d) {
     if (d.por) return false;  // the face coefficients carry dtx of BOTH cells of a face: uniform pore volume only
-    if (d.Ny % 64 != 0) return false;
-    const int W = d.Ny % 128 == 0 ? 128 : 64;
-    return d.Ny / W <= 16;
+    const int W = tb_tile_cols(d.Ny);
+    return W > 0 && d.Ny / W <= 16;
 }
 
 static int tb_launch_cfg(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int W, int csize, unsigned grid,
@@ -335,7 +486,7 @@ int transport_tb(hm_ctx* ctx, const hm_sim_desc& d, const Fluid& fl, const Wells
     *Sresult = Scur;
     *launches = 0;
     if (max_nts <= 0) return HM_OK;  // no flow in any member
-    const int W = d.Ny % 128 == 0 ? 128 : 64;
+    const int W = tb_tile_cols(d.Ny);
     const int R = kTbCells / W, cy = d.Ny / W;
     const bool unit = fl.inv_range == 1.0 && fl.swc_ir == 0.0 && fl.mr == 1.0;
     tb_fn kern = tb_kernel(W, unit);
@@ -350,7 +501,7 @@ int transport_tb(hm_ctx* ctx, const hm_sim_desc& d, const Fluid& fl, const Wells
     for (int cx = 1; cx <= std::min(cx_need, 16 / cy); ++cx) {
         if (d.tb_cluster_rows > 0 && cx != std::min(d.tb_cluster_rows, std::min(cx_need, 16 / cy))) continue;
         const int csize = cx * cy;
-        int& active = ctx->tb_active[W == 128][unit][csize];
+        int& active = ctx->tb_active[W == 512 ? 3 : W == 256 ? 2 : W == 128][unit][csize];
         if (active == 0) {
             cudaLaunchConfig_t cfg;
             cudaLaunchAttribute attr[1];
@@ -369,7 +520,7 @@ int transport_tb(hm_ctx* ctx, const hm_sim_desc& d, const Fluid& fl, const Wells
             tb_strips(d.Nx, R, cx, k, &nStrips, &stride);
             const double waves = std::ceil((double)nm * nStrips / active);
             const double rounds = single ? 1.0 : std::ceil((double)max_nts / k);
-            const double per_round = (single ? max_nts : k) * 0.5 + 3.0;
+            const double per_round = (single ? max_nts : k) * 0.8 + 1.5;  // us per work item: sub-steps + staging / set-up
             const double cost = waves * rounds * per_round;
             if (cost < best_cost) best_cost = cost, best_cx = cx, best_k = single ? 0 : k, best_active = active;
             if (single) break;
@@ -405,7 +556,8 @@ int transport_tb(hm_ctx* ctx, const hm_sim_desc& d, const Fluid& fl, const Wells
                 best_active * csize, ctx->sm_count);
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
-    tb_launch_cfg(&cfg, attr, W, csize, (unsigned)(nm * a.nStrips * csize), st);
+    a.nWork = nm * a.nStrips;
+    tb_launch_cfg(&cfg, attr, W, csize, (unsigned)(std::min(a.nWork, best_active) * csize), st);
     const int kround = a.nStrips == 1 ? max_nts : a.halo;
     int n_launch = 0;
     for (int it0 = 0; it0 < max_nts; it0 += kround, ++n_launch) {

@@ -74,5 +74,31 @@ def gaussian_fields_separable(grid, N=1, r=0.2, rng=None, device=None):
     gen = torch.Generator(device=device)
     gen.manual_seed(int(rng.randint(2**31 - 1)))
     Z = torch.randn((N, grid.Nx, grid.Ny), dtype=torch.float64, device=device, generator=gen)
-    Fx_d, Fy_d = torch.as_tensor(Fx, device=device), torch.as_tensor(Fy, device=device)
-    return (Fx_d @ Z @ Fy_d.T).reshape(N, -1)
+    return separable_apply(Fx, Z, Fy).reshape(N, -1)
+
+
+def separable_apply(Fx, Z, Fy):
+    """``Fx @ Z[n] @ Fy.T`` for every member ``n`` of the CUDA tensor ``Z (N, Nx, Ny)`` with the library's FP64
+    tensor-core GEMM (``hm_dgemm``): one product for all members on the right, one per member on the left."""
+    import ctypes as C
+
+    import torch
+
+    from historymatching_b200 import _lib
+
+    N, Nx, Ny = Z.shape
+    dev = Z.device
+    ctx = _lib.Context.get(dev.index if dev.index is not None else torch.cuda.current_device())
+    ctx.use_torch_stream()
+    Fx_d = torch.as_tensor(np.ascontiguousarray(Fx), dtype=torch.float64, device=dev)
+    Fy_d = torch.as_tensor(np.ascontiguousarray(Fy), dtype=torch.float64, device=dev)
+    Z = Z.contiguous()
+    Y = torch.empty_like(Z)
+    out = torch.empty_like(Z)
+    p = lambda t, off=0: C.c_void_p(t.data_ptr() + 8 * off)  # noqa: E731
+    # Y = Z Fy^T for all members at once: (N Nx, Ny) x (Ny, Ny)^T
+    _lib.check(ctx.lib.hm_dgemm(ctx.handle, 0, 1, N * Nx, Ny, Ny, 1.0, p(Z), Ny, p(Fy_d), Ny, 0.0, p(Y), Ny))
+    for n in range(N):  # out[n] = Fx Y[n]
+        _lib.check(ctx.lib.hm_dgemm(ctx.handle, 0, 0, Nx, Ny, Nx, 1.0, p(Fx_d), Nx, p(Y, n * Nx * Ny), Ny, 0.0,
+                                    p(out, n * Nx * Ny), Ny))
+    return out

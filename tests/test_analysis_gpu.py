@@ -254,3 +254,76 @@ def test_cov_corr_against_reference_golden(golden):
     g = golden("primitives.npz")
     np.testing.assert_allclose(ha.cov(g["E"], g["b"]), g["cov"], rtol=1e-11, atol=1e-13)
     np.testing.assert_allclose(ha.corr(g["E"], g["b"][:, 0]), g["corr"], rtol=1e-11, atol=1e-13)
+
+
+# ---- device entry points that round 1 exercised only indirectly ------------------------------------------------
+@pytest.mark.parametrize("rescale", [False, True])
+def test_center_device_vs_reference(golden, rescale):
+    """analysis.center on the device (hm_center), with and without the sqrt(N/(N-1)) rescaling (tools/utils.py:10-28)."""
+    import torch
+
+    from historymatching_b200 import analysis as ha
+
+    rng = np.random.RandomState(3)
+    E = rng.randn(37, 3, 50) * 3 + rng.randn(3, 50)
+    X, x = ha.center(E, rescale=rescale)
+    Xr, xr = oa.center(E, rescale=rescale)
+    np.testing.assert_allclose(X, Xr, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(x, xr, rtol=1e-13, atol=1e-13)
+    Xd, xd = ha.center(torch.as_tensor(E[:, 0], device="cuda"), rescale=rescale)   # CUDA tensors in -> CUDA tensors out
+    assert Xd.is_cuda and xd.is_cuda
+    Xr, xr = oa.center(E[:, 0], rescale=rescale)
+    np.testing.assert_allclose(Xd.cpu().numpy(), Xr, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(xd.cpu().numpy(), xr, rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize("sharpness", [1, 10, 0.5])
+def test_bump_taper_sharpness(sharpness):
+    """hm_taper_bump with sharpness != 1 (loc.bump(distances, sharpness), tools/localization.py:86-92)."""
+    from historymatching_b200 import analysis as ha
+
+    rng = np.random.RandomState(5)
+    xy_prm = rng.rand(300, 2) * [2, 1]
+    xy_obs = rng.rand(12, 2) * [2, 1]
+    ref = oa.bump(oa.pairwise_distances(xy_prm, xy_obs) / 0.7, sharpness)
+    np.testing.assert_allclose(ha.bump_taper(xy_prm, xy_obs, 0.7, sharpness), ref, rtol=1e-10, atol=1e-14)
+
+
+def test_es_update_host_entry_point():
+    """hm_es_update_host: the call a non-CUDA host makes (host pointers in, posterior written in place)."""
+    import ctypes as C
+
+    from historymatching_b200 import _lib
+
+    kw, _, _ = _hm_case(24, 130, 16, seed=2)
+    E = np.ascontiguousarray(kw["prior_ens"]).copy()
+    ctx = _lib.Context.get()
+    ptr = lambda a: C.c_void_p(np.ascontiguousarray(a).ctypes.data)  # noqa: E731
+    Eo, obs, pert, dec = (np.ascontiguousarray(kw[k]) for k in ("obs_ens", "obs", "perturbs", "decorr"))
+    _lib.check(ctx.lib.hm_es_update_host(ctx.handle, 24, 130, 16, C.c_void_p(E.ctypes.data), ptr(Eo), ptr(obs), ptr(pert),
+                                         ptr(dec)))
+    np.testing.assert_allclose(E, oa.ens_update0(**kw), **TOL)
+
+
+def test_separable_prior_on_device():
+    """gaussian_fields_separable(device=...): the two products Fx Z Fy^T through hm_dgemm equal the numpy einsum on the
+    same draw; the fields have the prescribed covariance structure (unit variance, correlation exp(-3 d^2 / r^2))."""
+    import torch
+
+    from historymatching_b200.dropin.tools import geostat
+    from historymatching_b200.sim import GridSpec
+
+    grid = GridSpec(48, 40, 2.0, 1.0)
+    r = 0.8
+    hx, hy = grid.Lx / grid.Nx, grid.Ly / grid.Ny
+    Fx = geostat._factor_1d((np.arange(grid.Nx) + 0.5) * hx, r)
+    Fy = geostat._factor_1d((np.arange(grid.Ny) + 0.5) * hy, r)
+    Z = torch.randn((7, grid.Nx, grid.Ny), dtype=torch.float64, device="cuda")
+    out = geostat.separable_apply(Fx, Z, Fy).cpu().numpy()
+    np.testing.assert_allclose(out, np.einsum("ia,nab,jb->nij", Fx, Z.cpu().numpy(), Fy), rtol=1e-12, atol=1e-12)
+    F = geostat.gaussian_fields_separable(grid, 4000, r=r, rng=np.random.RandomState(3), device="cuda")
+    assert F.is_cuda and F.shape == (4000, grid.M)
+    F = F.cpu().numpy().reshape(4000, grid.Nx, grid.Ny)
+    assert abs(F.var(0).mean() - 1) < 0.05
+    c = np.mean(F[:, 10, 10] * F[:, 16, 10])   # 6 cells apart in x
+    assert abs(c - np.exp(-3 * (6 * hx) ** 2 / r**2)) < 0.06
