@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-update-bench", action="store_true")
+    ap.add_argument("--no-config-d", action="store_true", help="skip the short BASELINE-config-4 (512x512) run")
+    ap.add_argument("--config-d-ntime", type=int, default=2, help="simulator steps of the short config-D run")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the baseline sample")
     ap.add_argument("--sat-block", type=int, default=0, help="transport kernel variant (hm_sim_desc.sat_block)")
     ap.add_argument("--precond", type=int, default=0, help="pressure preconditioner (hm_sim_desc.precond)")
@@ -317,6 +319,36 @@ def main():
         # NCCL writes its version / debug lines to stdout by default; stdout carries the one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
+    line = measure(args, wl, rank, world, local_rank, dev, args.steps, args.warmup, full=True)
+    if args.workload == "C" and not args.no_config_d and not args.members and not args.ntime:
+        # BASELINE config 4 (the north-star size): 512 x 512, 512 members per GPU (4096 on 8 GPUs), a SHORT run - nTime
+        # simulator steps instead of 40, stated in the block - with the sharded ES update over NCCL included
+        wd = dict(WORKLOADS["D"], nTime=args.config_d_ntime)
+        d = measure(args, wd, rank, world, local_rank, dev, steps=1, warmup=1, full=False)
+        if rank == 0:
+            per_step_s = d["ms_per_step"] / 1e3 / wd["nTime"]
+            d["projected"] = dict(
+                seconds_per_simulator_step=per_step_s,
+                seconds_per_40_step_pass=40 * (per_step_s - d["update_ms"] / 1e3 / wd["nTime"]) + d["update_ms"] / 1e3,
+                seconds_per_es_mda_cycle_Na4=4 * (40 * (per_step_s - d["update_ms"] / 1e3 / wd["nTime"]) + d["update_ms"] / 1e3),
+                note="forward time is linear in the number of simulator steps (the sub-step count per step is constant, "
+                     "SURVEY.md A.5); one complete 40-step pass measured on 8 GPUs: profiles/bench_r2_configD_8gpu_full.json")
+            line["config_d"] = d
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure(args, wl, rank, world, local_rank, dev, steps, warmup, full):
+    """One workload: warm-up passes, `steps` timed passes, the roofline of its dominant kernel.  full: also the end-to-end
+    number through host buffers, the update benchmarks and the CPU baseline (the headline workload)."""
+    import torch
+    import torch.distributed as dist
+
+    args = argparse.Namespace(**{**vars(args), "steps": steps, "warmup": warmup})
+    if not full:
+        args.no_e2e = args.no_update_bench = args.no_cpu_baseline = True
     from historymatching_b200 import _lib
     from historymatching_b200 import analysis as ha
     from historymatching_b200 import dist as hd
@@ -353,8 +385,10 @@ def main():
         last["res"] = res
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()  # the ranks' forward runs end at slightly different times: keep that wait out of update_ms
         t0.record()
-        post = hd.sharded_update(ha.ens_update0, E, Eo, N, obs=noisy, perturbs=pert, decorr=dec)
+        post = hd.es_update_sharded(E, Eo, N, noisy, pert, dec)
         t1.record()
         last["upd"] = (t0, t1)
         return post, Eo
@@ -382,7 +416,7 @@ def main():
     ev0.record()
     phase = dict(setup=0.0, cg=0.0, flux=0.0, saturation=0.0, obs=0.0)
     upd_ms, cg_member_iters, sat_member_substeps = 0.0, 0, 0
-    stats_acc = dict(cg_kernel_launches=0, sat_kernel_launches=0, mg_fp64_fallbacks=0, kernel_launches=0)
+    stats_acc = dict(cg_kernel_launches=0, sat_kernel_launches=0, mg_fp64_fallbacks=0, kernel_launches=0, sat_cell_updates=0)
     torch.cuda.nvtx.range_push("timed")  # lets ncu select the timed region (--nvtx --nvtx-include "timed/")
     for _ in range(args.steps):
         post, Eo = one_pass(E0)
@@ -426,7 +460,7 @@ def main():
             pr = pert_host.to(dev, non_blocking=True)
             ob = noisy_host.to(dev, non_blocking=True)
             Eo, _ = case.forward(E, sat_block=args.sat_block, precond=args.precond, lanes=args.lanes)
-            post = hd.sharded_update(ha.ens_update0, E, Eo, N, obs=ob, perturbs=pr, decorr=dec)
+            post = hd.es_update_sharded(E, Eo, N, ob, pr, dec)
             out_host.copy_(post, non_blocking=True)
             eo_host.copy_(Eo, non_blocking=True)
 
@@ -445,9 +479,7 @@ def main():
                    d2h_bytes_per_step=int(8 * (out_host.numel() + eo_host.numel())))
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
     # Algorithmic HBM bytes: a transport sub-step streams 32 B/cell
@@ -456,10 +488,17 @@ def main():
     pk, pk_kind = peaks()
     hbm = float(pk.get("hbm_gbs", PEAKS_FALLBACK["hbm_gbs"]))
     pcg_name = "MG-PCG iteration (k_mg_down+k_mg_onchip+k_mg_up+k_cg_spmv+k_cg_update)"
-    cluster = stats_acc["sat_kernel_launches"] <= args.steps * wl["nTime"]  # one launch per time step
+    st_last = last["res"].stats
+    tb = int(st_last.get("sat_tb_cluster", 0)) > 0            # temporally blocked kernel k_sat_tb (hm_transport.cu)
+    cluster = not tb and stats_acc["sat_kernel_launches"] <= args.steps * wl["nTime"]  # k_sat_cluster: one launch per time step
     stream_name = ("k_sat_stream (one sub-step per launch, tile staged by bulk copies)"
                    if wl["Ny"] % 2 == 0 and args.sat_block != 5 else "k_sat_substep (one sub-step per launch, plain loads)")
     sat_name = "k_sat_cluster (all CFL sub-steps of a time step, register/DSMEM resident)" if cluster else stream_name
+    if tb:
+        sat_name = ("k_sat_tb (temporally blocked: %d-CTA clusters, 4096 cells per CTA in registers, %s)"
+                    % (st_last["sat_tb_cluster"], "all CFL sub-steps of a time step in one launch" if st_last["sat_tb_strips"] == 1
+                       else "%d overlapping row strips per member, %d sub-steps per HBM round trip"
+                       % (st_last["sat_tb_strips"], st_last["sat_tb_halo"])))
     # FP64 cycle: k_mg_down 50 + k_mg_up 60 + k_cg_spmv 48 + k_cg_update 48 = 206 B; FP32 cycle (the default): the cycle's
     # operators and iterates are 4-byte, k_mg_down 25 (r 8, 1/diag 4, TX TY 8, x 4, coarse rhs 1) + k_mg_up 33 = 154 B
     pcg_bytes_per_cell = 154.0 if (args.precond in (0, 3) and stats_acc["mg_fp64_fallbacks"] == 0) else 206.0
@@ -482,34 +521,49 @@ def main():
                     traffic=None, peak_source=pk_kind + (" burst" if pk_kind == "measured" else ""),
                     algorithmic_bytes_per_launch=b / max(1, n_launch), avg_launch_ms=t_ms / max(1, n_launch),
                     share_of_step=t_ms / ms)
-    if dom == sat_name and cluster:
-        # the cluster kernel touches HBM once per time step (40 B/cell: S in, 3 flux reads incl. pads, S out),
-        # the streaming model above counts 32 B per sub-step: frac > 1 is on-chip reuse
+    if dom == sat_name and (cluster or tb):
+        # On-chip transport kernels: the streaming model above counts 32 B per cell and sub-step, the kernels touch HBM once
+        # per time step (k_sat_cluster, k_sat_tb with one strip: 40 B/cell: S in, 3 flux reads incl. pads, S out) or once per
+        # round of k sub-steps (k_sat_tb on row strips): frac > 1 is on-chip reuse.  What binds them is on-chip; peaks
+        # MEASURED on this GPU (profiles/tools/probe_fp64.cu, profiles/probe_r1.txt): FP64 pipe 61.5 lanes/clk/SM (DFMA: 2.08
+        # cycles per warp instruction and SM sub-partition), shared-memory crossbar 128 B/clk/SM.
         nts_mean = sat_member_substeps / max(1, N_loc * wl["nTime"] * args.steps)
         sm_hz = (sampler.summary()["sm_mhz"] or 1965.0) * 1e6
-        roofline["on_chip_reuse_factor"] = 32.0 * nts_mean / 40.0
-        roofline["hbm_bytes_per_launch_actual"] = 40.0 * M * N_loc
-        # The binding resources, against peaks MEASURED on this GPU (profiles/tools/probe_fp64.cu, profiles/probe_r1.txt):
-        # FP64 pipe 61.5 lanes/clk/SM (DFMA: 2.08 cycles per warp instruction and SM sub-partition); the shared-memory
-        # crossbar 128 B/clk/SM (LDS.64: 2.04 cycles per warp instruction).  Per cell and sub-step the kernel issues 13
-        # FP64 instructions and moves 32 B through shared memory (1 store + 3 loads of fw).
         sm_n = 148
-        resident = int(last["res"].stats.get("sat_resident_ctas", 0))
-        roofline["fp64_pipe_frac"] = 13.0 * M * sat_member_substeps / (t_ms * 1e-3) / (sm_n * 61.5 * sm_hz)
+        resident = int(st_last.get("sat_resident_ctas", 0))
+        if tb:
+            # per cell and sub-step: 11 FP64 instructions (7 fw + 4 face FMAs), 20 B through shared memory (1 store + 1.5
+            # loads of fw); redundant halo-row updates of overlapping strips are executed work, not useful work
+            fp64_per_cell, smem_per_cell = 11.0, 20.0
+            executed = stats_acc["sat_cell_updates"]
+            useful = float(M) * sat_member_substeps
+            strips, halo = int(st_last["sat_tb_strips"]), int(st_last["sat_tb_halo"])
+            rounds = 1.0 if strips == 1 else nts_mean / halo
+            rows_loaded = executed / max(useful, 1.0)                    # strip rows loaded per grid row
+            hbm_actual = 8.0 * M * N_loc * rounds * (3.0 * rows_loaded + 1.0)  # S + 2 fluxes in (with overlap), S out
+            roofline["redundancy"] = executed / max(useful, 1.0)
+            roofline["cell_updates_per_s"] = dict(useful=useful / (t_ms * 1e-3), executed=executed / (t_ms * 1e-3))
+        else:
+            fp64_per_cell, smem_per_cell = 13.0, 32.0
+            executed = useful = float(M) * sat_member_substeps
+            hbm_actual = 40.0 * M * N_loc
+        roofline["on_chip_reuse_factor"] = 32.0 * M * N_loc * nts_mean / hbm_actual
+        roofline["hbm_bytes_per_time_step_actual"] = hbm_actual
+        roofline["hbm_actual_GBps"] = hbm_actual * wl["nTime"] * args.steps / (t_ms * 1e-3) / 1e9
+        roofline["fp64_pipe_frac"] = fp64_per_cell * executed / (t_ms * 1e-3) / (sm_n * 61.5 * sm_hz)
         smem_peak = sm_n * 128.0 * sm_hz / 1e9
-        smem_ach = 32.0 * M * sat_member_substeps / (t_ms * 1e-3) / 1e9
+        smem_ach = smem_per_cell * executed / (t_ms * 1e-3) / 1e9
         roofline["smem_crossbar"] = dict(achieved=smem_ach, peak=smem_peak, unit="GB/s", frac=smem_ach / smem_peak)
         roofline["resident_ctas"] = resident
         roofline["sm_coverage"] = min(1.0, resident / sm_n) if resident else None
-        roofline["note"] = ("streaming model of SURVEY 8(d) (32 B per cell and sub-step); the kernel keeps S and the upwind "
-                            "coefficients in registers for all sub-steps of a time step and touches HBM once per time step, "
-                            "so frac > 1 is the on-chip reuse factor at work.  What binds it is on-chip: the shared-memory "
-                            "crossbar (fw exchange, smem_crossbar.frac) and the FP64 pipe (fp64_pipe_frac), which alternate "
-                            "around the one CTA barrier per sub-step, on the SMs the 8-CTA clusters can occupy (sm_coverage)")
-        prof = os.path.join(ROOT, "profiles", "ncu_k_sat_cluster.json")
+        roofline["note"] = ("streaming model of SURVEY 8(d) (32 B per cell and sub-step); the kernel keeps S and the face "
+                            "coefficients in registers for many sub-steps, so frac > 1 is the on-chip reuse factor at work.  "
+                            "What binds it is on-chip: the FP64 pipe (fp64_pipe_frac, of all 148 SMs), the shared-memory "
+                            "crossbar (smem_crossbar.frac) and the SMs its clusters can occupy (sm_coverage)")
+        prof = os.path.join(ROOT, "profiles", "ncu_k_sat_tb.json" if tb else "ncu_k_sat_cluster.json")
         if os.path.exists(prof) and (wl["Nx"], wl["Ny"], N_loc) == (128, 128, 1024):
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch at exactly this configuration
-            # (ncu --set full capture, profiles/ncu_k_sat_cluster.txt)
+            # (ncu --set full capture, profiles/ncu_k_sat_*.txt)
             roofline["traffic"] = json.load(open(prof))[0]["traffic_MB"] * 1e6
     other = sat_name if dom != sat_name else pcg_name
     ob, ot, _ = cands[other]
@@ -536,9 +590,7 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         v, cores, sample = cpu_forward_sample(wl, args.cpu_seconds)
         line["cpu_baseline"] = dict(value=v, unit="member*steps/s", cores=cores, kind="port", sample=sample)
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 if __name__ == "__main__":

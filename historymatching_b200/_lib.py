@@ -84,6 +84,7 @@ SYMBOLS = {
     "hm_iles_step": (C.c_int, [C.c_void_p, i64, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_double]),
     "hm_iles_recompose": (C.c_int, [C.c_void_p, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hm_copy2d": (C.c_int, [C.c_void_p, i64, i64, C.c_void_p, i64, C.c_void_p, i64]),
     "hm_corr": (C.c_int, [C.c_void_p, i64, i64, i64, C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, C.c_int]),
 }
 

@@ -695,3 +695,29 @@ extern "C" int hm_corr(hm_ctx* ctx, int64_t N, int64_t M, int64_t q, const doubl
     HM_CUDA(cudaGetLastError());
     return HM_OK;
 }
+
+// ---- strided block copy: the pack / unpack step of the member <-> parameter-column re-sharding --------------------
+namespace {
+__global__ void __launch_bounds__(256) k_copy2d(int64_t rows, int64_t cols, const double* __restrict__ src, int64_t lds,
+                                                double* __restrict__ dst, int64_t ldd) {
+    const int64_t n = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols, c = i - r * cols;
+        dst[r * ldd + c] = src[r * lds + c];
+    }
+}
+}  // namespace
+
+extern "C" int hm_copy2d(hm_ctx* ctx, int64_t rows, int64_t cols, const double* src, int64_t lds, double* dst,
+                         int64_t ldd) {
+    HM_REQUIRE(ctx, "null ctx");
+    if (rows <= 0 || cols <= 0) return HM_OK;
+    HM_REQUIRE(src && dst && lds >= cols && ldd >= cols, "pointers / row strides");
+    HM_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n = rows * cols;
+    const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
+    k_copy2d<<<grid, 256, 0, ctx->stream>>>(rows, cols, src, lds, dst, ldd);
+    ctx->launches += 1;
+    HM_CUDA(cudaGetLastError());
+    return HM_OK;
+}

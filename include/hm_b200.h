@@ -226,6 +226,11 @@ int hm_iles_recompose(hm_ctx* ctx, int64_t N, int64_t M, const double* Ws, const
 int hm_corr(hm_ctx* ctx, int64_t N, int64_t M, int64_t q, const double* a, int64_t lda,
             const double* b, int64_t ldb, double* out, int corr);
 
+/* Strided block copy dst[r*ldd + c] = src[r*lds + c], rows x cols (device pointers): the pack / unpack step of the
+ * member-row <-> parameter-column re-sharding around the all-to-all of the multi-GPU analysis (SURVEY.md section 8(e);
+ * the reference has no counterpart - its ensemble lives in one process, tools/utils.py:155-242). */
+int hm_copy2d(hm_ctx* ctx, int64_t rows, int64_t cols, const double* src, int64_t lds, double* dst, int64_t ldd);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,8 +49,27 @@ def _worker(rank, size, port, N, M, p, out):
     ref_loc = oa.ens_update0_loc(E, Eo, obs, pert, dec, taper)
     ok = np.allclose(post.numpy(), ref[lo:hi], rtol=1e-10, atol=1e-12)
     ok_loc = np.allclose(post_loc.numpy(), ref_loc[lo:hi], rtol=1e-10, atol=1e-12)
+    # the sharded ES-MDA cycle (host logic + collectives); the CUDA update is stood in by the oracle on CPU
+    from historymatching_b200 import analysis as ha
+
+    ha.ens_update0 = lambda Ec, Eof, obs, perturbs, decorr: torch.as_tensor(  # noqa: E731
+        oa.ens_update0(Ec.numpy(), Eof.numpy(), np.asarray(obs), np.asarray(perturbs), np.asarray(decorr)))
+    H = rng.randn(M, p) / 3
+    R12 = np.linalg.cholesky(0.01 * (np.eye(p) + 0.3 * np.ones((p, p))))
+    Zs = [rng.randn(N, p) for _ in range(2)]
+    post_mda, st = hd.es_mda_sharded(lambda X: torch.tanh(X @ torch.as_tensor(H)), E_loc, N, obs, R12, [2.0, 2.0],
+                                     perturbs=Zs)
+    Er = E.copy()
+    for Z, a in zip(Zs, [2.0, 2.0]):
+        Er = oa.ens_update0(Er, np.tanh(Er @ H), obs, np.sqrt(a) * (Z @ R12.T), np.linalg.inv(R12.T) / np.sqrt(a))
+    ok_mda = np.allclose(post_mda.numpy(), Er[lo:hi], rtol=1e-10, atol=1e-12) and len(st["Eo"]) == 2
+    # the seeded perturbations are the same block on every rank
+    zz = hd._normal_block(N, p, 5, "cpu")
+    gathered = [torch.empty_like(zz) for _ in range(size)]
+    dist.all_gather(gathered, zz)
+    ok_mda = ok_mda and all(torch.equal(g, zz) for g in gathered)
     with open(os.path.join(out, f"rank{rank}"), "w") as f:
-        f.write(str(int(ok and ok_loc)))
+        f.write(str(int(ok and ok_loc and ok_mda)))
     dist.destroy_process_group()
 
 
@@ -58,6 +77,13 @@ def test_sharded_update_world2_gloo(tmp_path):
     size = 2
     mp.spawn(_worker, args=(size, _free_port(), 7, 11, 5, str(tmp_path)), nprocs=size, join=True)
     assert [open(tmp_path / f"rank{r}").read() for r in range(size)] == ["1", "1"]
+
+
+def test_sharded_update_world3_gloo_even_blocks(tmp_path):
+    """Three ranks, equal member blocks (the all_gather_into_tensor path) and uneven column blocks."""
+    size = 3
+    mp.spawn(_worker, args=(size, _free_port(), 9, 10, 4, str(tmp_path)), nprocs=size, join=True)
+    assert [open(tmp_path / f"rank{r}").read() for r in range(size)] == ["1", "1", "1"]
 
 
 def test_single_process_is_identity():

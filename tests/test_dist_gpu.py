@@ -57,8 +57,17 @@ def _worker(rank, size, port, out):
                                  decorr=dec, taper=taper[clo:chi].contiguous())
     ref_loc = ha.ens_update0_loc(E, Eo_full, obs=obs, perturbs=pert, decorr=dec, taper=taper)
     ok = ok and torch.allclose(post_loc, ref_loc[lo:hi], rtol=1e-10, atol=1e-12)
+    # the sharded cycles (product API) against the single-device functions on the full ensemble
+    fwd_loc = lambda X: case.forward(X.contiguous())[0]  # noqa: E731
+    Zs = [rng.randn(N, p) for _ in range(2)]
+    post_mda, st = hd.es_mda_sharded(fwd_loc, E[lo:hi].contiguous(), N, obs, case.R12, [2.0, 2.0], perturbs=Zs)
+    ref_mda, _ = ha.es_mda(E, lambda X: case.forward(X)[0], obs.cpu().numpy(), case.R12, [2.0, 2.0], perturbs=Zs)
+    ok_mda = torch.allclose(post_mda, ref_mda[lo:hi], rtol=1e-8, atol=1e-10) and len(st["Eo"]) == 2
+    post_ies, st = hd.ies_sharded(fwd_loc, E[lo:hi].contiguous(), N, obs, pert, dec, xStep=0.6, iMax=3)
+    ref_ies, _ = ha.IES(E, lambda X: case.forward(X)[0], obs, pert, dec, xStep=0.6, iMax=3)
+    ok_ies = torch.allclose(post_ies, ref_ies[lo:hi], rtol=1e-8, atol=1e-10) and len(st["Eo"]) == 3
     with open(os.path.join(out, f"rank{rank}"), "w") as f:
-        f.write(str(int(ok)))
+        f.write(f"{int(ok)}{int(ok_mda)}{int(ok_ies)}")
     dist.destroy_process_group()
 
 
@@ -69,4 +78,4 @@ def test_sharded_forward_and_update_world2_nccl(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
-    assert [open(tmp_path / f"rank{r}").read() for r in range(2)] == ["1", "1"]
+    assert [open(tmp_path / f"rank{r}").read() for r in range(2)] == ["111", "111"]  # update, ES-MDA, IES
