@@ -85,6 +85,7 @@ SYMBOLS = {
                                C.c_void_p, C.c_void_p, C.c_double]),
     "hm_iles_recompose": (C.c_int, [C.c_void_p, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hm_copy2d": (C.c_int, [C.c_void_p, i64, i64, C.c_void_p, i64, C.c_void_p, i64]),
+    "hm_swap01": (C.c_int, [C.c_void_p, i64, i64, i64, C.c_void_p, C.c_void_p]),
     "hm_corr": (C.c_int, [C.c_void_p, i64, i64, i64, C.c_void_p, i64, C.c_void_p, i64, C.c_void_p, C.c_int]),
 }
 

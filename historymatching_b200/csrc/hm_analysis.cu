@@ -15,6 +15,8 @@
 //    and a Cholesky solve replaces the SVD pseudo-inverse.
 //  * ES is evaluated as E + (D C^-1)(S^T E): 4 N p M flops instead of the
 //    reference's left-to-right 2 N^2 M.
+#include <algorithm>
+
 #include "hm_common.cuh"
 
 namespace hm {
@@ -24,6 +26,8 @@ int dgemm(hm_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_t k, double
 }
 
 namespace {
+
+constexpr size_t kMaxWorkSmem = 227 * 1024;  // dynamic shared memory a CTA can opt into on sm_100
 
 int ensure_solver(hm_ctx* ctx) {
     if (!ctx->solver) {
@@ -121,9 +125,12 @@ __global__ void k_taper_bump(int64_t M, int64_t p, const double* __restrict__ xy
 __global__ void __launch_bounds__(256)
 k_local_analysis(int64_t M, int p, double nm1, const double* __restrict__ A,
                  const double* __restrict__ taper, double* __restrict__ B, int64_t ldB,
-                 int* __restrict__ fail) {
-    extern __shared__ double sm[];
-    const int64_t i = blockIdx.x;
+                 int* __restrict__ fail, double* gws, size_t gws_stride) {
+    // Workspace: dynamic shared memory where the tapered p x p system fits (p <= 165), otherwise this CTA's slab of
+    // a global-memory workspace (L1 / L2 resident; the CTA barrier orders its accesses) - same algorithm, no size limit.
+    extern __shared__ double sm_dyn[];
+    double* sm = gws ? gws + blockIdx.x * gws_stride : sm_dyn;
+    for (int64_t i = blockIdx.x; i < M; i += gridDim.x) {
     double* c = sm;           // [p] sqrt(taper) of active obs
     double* rhs = sm + p;     // [p]
     int* idx = (int*)(sm + 2 * p);  // [p] active obs indices
@@ -191,6 +198,8 @@ k_local_analysis(int64_t M, int p, double nm1, const double* __restrict__ A,
     __syncthreads();
     for (int a = tid; a < n; a += nt) B[(int64_t)idx[a] * ldB + i] = c[a] * rhs[a];
     if (tid == 0 && s_fail) atomicExch(fail, 1);
+    __syncthreads();  // the workspace is reused by this CTA's next parameter
+    }
 }
 
 // ---- batched localised IES step (HistoryMatch.py:1034-1059) -------------------------------------
@@ -200,11 +209,16 @@ k_local_analysis(int64_t M, int p, double nm1, const double* __restrict__ A,
 //   (= the inverse of the reference's SVD expression for covw), Cholesky of C, dW = G C^-1,
 //   Wi += xStep dW.  Si / Di are the tapered, active columns of S / D as in k_local_analysis.
 __global__ void __launch_bounds__(256)
-k_iles_step(int N, int p, double xStep, const double* __restrict__ S, const double* __restrict__ D,
-            const double* __restrict__ taper, double* __restrict__ Ws, int* __restrict__ fail) {
-    extern __shared__ double sm[];
-    const int64_t ip = blockIdx.x;
+k_iles_step(int N, int64_t M, int p, double xStep, const double* __restrict__ S, const double* __restrict__ D,
+            const double* __restrict__ taper, double* __restrict__ Ws, int* __restrict__ fail, double* gws,
+            size_t gws_stride) {
+    // Workspace (3 N^2 + N p doubles): dynamic shared memory where it fits (N <= ~72 at p = 160), otherwise this CTA's slab
+    // of a global-memory workspace - same algorithm, no size limit (the notebook's N = 200 runs this way).
+    extern __shared__ double sm_dyn[];
+    double* sm = gws ? gws + blockIdx.x * gws_stride : sm_dyn;
     const int tid = threadIdx.x, nt = blockDim.x;
+    for (int64_t ip = blockIdx.x; ip < M; ip += gridDim.x) {
+    __syncthreads();  // the workspace and the flags are reused by this CTA's next parameter
     double* A = sm;                 // N*N  : Wi -> Wi^-1 -> centred
     double* G = A + N * N;          // N*N
     double* Cc = G + N * N;         // N*N
@@ -232,7 +246,7 @@ k_iles_step(int N, int p, double xStep, const double* __restrict__ S, const doub
     }
     __syncthreads();
     const int n = s_n;
-    if (n == 0) return;  // no active observation: dW = 0 (HistoryMatch.py:1039-1040)
+    if (n == 0) continue;  // no active observation: dW = 0 (HistoryMatch.py:1039-1040)
     for (int e = tid; e < N * N; e += nt) A[e] = W[e];
     __syncthreads();
     // in-place Gauss-Jordan inversion with partial pivoting
@@ -362,6 +376,7 @@ k_iles_step(int N, int p, double xStep, const double* __restrict__ S, const doub
     __syncthreads();
     for (int e = tid; e < N * N; e += nt) W[e] = fma(xStep, G[e], W[e]);
     if (tid == 0 && s_fail) atomicExch(fail, 1);
+    }
 }
 
 // E[:, i] = x0[i] + Ws[i] X0[:, i]   (recompose, HistoryMatch.py:1020-1021)
@@ -511,8 +526,7 @@ extern "C" int hm_les_update(hm_ctx* ctx, int64_t N, int64_t M, int64_t p, doubl
     HM_REQUIRE(ctx && E && Eo && obs && perturbs && decorr && taper, "null pointer");
     HM_REQUIRE(N > 1 && M > 0 && p > 0 && ldE >= M, "shape");
     HM_CUDA(cudaSetDevice(ctx->device));
-    const size_t smem = ((size_t)2 * p + (p + 1) / 2 + (size_t)p * p) * sizeof(double);
-    HM_REQUIRE(smem <= 227 * 1024, "p too large for the shared-memory local analysis (p <= 165)");
+    size_t smem = ((size_t)2 * p + (p + 1) / 2 + (size_t)p * p) * sizeof(double);
     double *S, *D, *A, *B;
     int* fail;
     HM_CHECK(whiten(ctx, N, p, Eo, obs, perturbs, decorr, &S, &D));
@@ -522,8 +536,17 @@ extern "C" int hm_les_update(hm_ctx* ctx, int64_t N, int64_t M, int64_t p, doubl
     HM_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), ctx->stream));
     HM_CHECK(hm::dgemm(ctx, true, false, p, p, N, 1.0, S, p, S, p, 0.0, A, p));
     HM_CHECK(hm::dgemm(ctx, true, false, p, M, N, 1.0, S, p, E, ldE, 0.0, B, M));
+    double* gws = nullptr;
+    size_t gstride = 0;
+    unsigned grid = (unsigned)M;
+    if (smem > kMaxWorkSmem) {  // the tapered system does not fit shared memory: global-memory workspace, persistent CTAs
+        gstride = (smem / sizeof(double) + 15) & ~(size_t)15;
+        grid = (unsigned)std::min<int64_t>(M, (int64_t)ctx->sm_count * 4);
+        HM_CHECK(ctx->ws.get("an.loc_ws", gstride * grid, &gws));
+        smem = 0;
+    }
     HM_CUDA(cudaFuncSetAttribute(k_local_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_local_analysis<<<(unsigned)M, 256, smem, ctx->stream>>>(M, (int)p, (double)(N - 1), A, taper, B, M, fail);
+    k_local_analysis<<<grid, 256, smem, ctx->stream>>>(M, (int)p, (double)(N - 1), A, taper, B, M, fail, gws, gstride);
     ctx->launches += 1;
     HM_CUDA(cudaGetLastError());
     HM_CHECK(hm::dgemm(ctx, false, false, N, M, p, 1.0, D, p, B, M, 1.0, E, ldE));
@@ -592,15 +615,23 @@ extern "C" int hm_iles_step(hm_ctx* ctx, int64_t N, int64_t M, int64_t p, double
     HM_REQUIRE(ctx && Ws && Eo && obs && perturbs && decorr && taper, "null pointer");
     HM_REQUIRE(N > 1 && M > 0 && p > 0, "shape");
     HM_CUDA(cudaSetDevice(ctx->device));
-    const size_t smem = ((size_t)3 * N * N + (size_t)N * p + p + N) * sizeof(double) + (size_t)(p + N) * sizeof(int);
-    HM_REQUIRE(smem <= 227 * 1024, "N, p too large for the shared-memory localised IES step (3 N^2 + N p doubles)");
+    size_t smem = ((size_t)3 * N * N + (size_t)N * p + p + N) * sizeof(double) + (size_t)(p + N) * sizeof(int);
     double *S, *D;
     int* fail;
     HM_CHECK(whiten(ctx, N, p, Eo, obs, perturbs, decorr, &S, &D));
     HM_CHECK(ctx->ws.get("an.info", (size_t)4, &fail));
     HM_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), ctx->stream));
+    double* gws = nullptr;
+    size_t gstride = 0;
+    unsigned grid = (unsigned)M;
+    if (smem > kMaxWorkSmem) {  // 3 N^2 + N p doubles do not fit shared memory: global-memory workspace, persistent CTAs
+        gstride = (smem / sizeof(double) + 15) & ~(size_t)15;
+        grid = (unsigned)std::min<int64_t>(M, (int64_t)ctx->sm_count * 4);
+        HM_CHECK(ctx->ws.get("an.loc_ws", gstride * grid, &gws));
+        smem = 0;
+    }
     HM_CUDA(cudaFuncSetAttribute(k_iles_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_iles_step<<<(unsigned)M, 256, smem, ctx->stream>>>((int)N, (int)p, xStep, S, D, taper, Ws, fail);
+    k_iles_step<<<grid, 256, smem, ctx->stream>>>((int)N, M, (int)p, xStep, S, D, taper, Ws, fail, gws, gstride);
     ctx->launches += 1;
     HM_CUDA(cudaGetLastError());
     return check_info(ctx, fail, "localised IES step (singular Wi or non-SPD Gauss-Newton matrix)");
@@ -717,6 +748,30 @@ extern "C" int hm_copy2d(hm_ctx* ctx, int64_t rows, int64_t cols, const double* 
     const int64_t n = rows * cols;
     const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
     k_copy2d<<<grid, 256, 0, ctx->stream>>>(rows, cols, src, lds, dst, ldd);
+    ctx->launches += 1;
+    HM_CUDA(cudaGetLastError());
+    return HM_OK;
+}
+
+// ---- swap of the two leading axes of a (d0, d1, d2) array: dst[j][i][:] = src[i][j][:] ------------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_swap01(int64_t d0, int64_t d1, int64_t d2, const double* __restrict__ src,
+                                                double* __restrict__ dst) {
+    const int64_t n = d0 * d1 * d2;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = e % d2, ij = e / d2, j = ij % d0, i = ij / d0;  // e indexes dst[i][j][k], i < d1, j < d0
+        dst[e] = src[(j * d1 + i) * d2 + k];
+    }
+}
+}  // namespace
+
+extern "C" int hm_swap01(hm_ctx* ctx, int64_t d0, int64_t d1, int64_t d2, const double* src, double* dst) {
+    HM_REQUIRE(ctx && src && dst && src != dst, "pointers");
+    if (d0 <= 0 || d1 <= 0 || d2 <= 0) return HM_OK;
+    HM_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n = d0 * d1 * d2;
+    const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
+    k_swap01<<<grid, 256, 0, ctx->stream>>>(d0, d1, d2, src, dst);
     ctx->launches += 1;
     HM_CUDA(cudaGetLastError());
     return HM_OK;

@@ -79,7 +79,8 @@ def gaussian_fields_separable(grid, N=1, r=0.2, rng=None, device=None):
 
 def separable_apply(Fx, Z, Fy):
     """``Fx @ Z[n] @ Fy.T`` for every member ``n`` of the CUDA tensor ``Z (N, Nx, Ny)`` with the library's FP64
-    tensor-core GEMM (``hm_dgemm``): one product for all members on the right, one per member on the left."""
+    tensor-core GEMM (``hm_dgemm``), three launches for the whole ensemble: the right factor on the ``(N Nx, Ny)``
+    view, a swap of the two leading axes (``hm_swap01``), the left factor on the ``(Nx, N Ny)`` view, and the swap back."""
     import ctypes as C
 
     import torch
@@ -93,12 +94,15 @@ def separable_apply(Fx, Z, Fy):
     Fx_d = torch.as_tensor(np.ascontiguousarray(Fx), dtype=torch.float64, device=dev)
     Fy_d = torch.as_tensor(np.ascontiguousarray(Fy), dtype=torch.float64, device=dev)
     Z = Z.contiguous()
-    Y = torch.empty_like(Z)
-    out = torch.empty_like(Z)
-    p = lambda t, off=0: C.c_void_p(t.data_ptr() + 8 * off)  # noqa: E731
-    # Y = Z Fy^T for all members at once: (N Nx, Ny) x (Ny, Ny)^T
-    _lib.check(ctx.lib.hm_dgemm(ctx.handle, 0, 1, N * Nx, Ny, Ny, 1.0, p(Z), Ny, p(Fy_d), Ny, 0.0, p(Y), Ny))
-    for n in range(N):  # out[n] = Fx Y[n]
-        _lib.check(ctx.lib.hm_dgemm(ctx.handle, 0, 0, Nx, Ny, Nx, 1.0, p(Fx_d), Nx, p(Y, n * Nx * Ny), Ny, 0.0,
-                                    p(out, n * Nx * Ny), Ny))
-    return out
+    A = torch.empty_like(Z)
+    B = torch.empty_like(Z)
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    # A[n, a, :] = Z[n, a, :] Fy^T            (N Nx, Ny) x (Ny, Ny)^T
+    _lib.check(ctx.lib.hm_dgemm(ctx.handle, 0, 1, N * Nx, Ny, Ny, 1.0, p(Z), Ny, p(Fy_d), Ny, 0.0, p(A), Ny))
+    # B[a, n, :] = A[n, a, :]
+    _lib.check(ctx.lib.hm_swap01(ctx.handle, N, Nx, Ny, p(A), p(B)))
+    # A[i, (n, :)] = sum_a Fx[i, a] B[a, (n, :)]   (Nx, Nx) x (Nx, N Ny)
+    _lib.check(ctx.lib.hm_dgemm(ctx.handle, 0, 0, Nx, N * Ny, Nx, 1.0, p(Fx_d), Nx, p(B), N * Ny, 0.0, p(A), N * Ny))
+    # out[n, i, :] = A[i, n, :]
+    _lib.check(ctx.lib.hm_swap01(ctx.handle, Nx, N, Ny, p(A), p(B)))
+    return B

@@ -231,6 +231,12 @@ int hm_corr(hm_ctx* ctx, int64_t N, int64_t M, int64_t q, const double* a, int64
  * the reference has no counterpart - its ensemble lives in one process, tools/utils.py:155-242). */
 int hm_copy2d(hm_ctx* ctx, int64_t rows, int64_t cols, const double* src, int64_t lds, double* dst, int64_t ldd);
 
+/* dst[j][i][:] = src[i][j][:] for a dense (d0, d1, d2) array (device pointers, out of place).  Used by the scalable
+ * separable prior sampler (the stand-in for geostat.gaussian_fields, tools/geostat.py:86-99, at grid sizes where its dense
+ * M x M covariance is infeasible): the left factor of Fx Z Fy^T is applied to all members in ONE GEMM on an
+ * (Nx, N, Ny) layout, this kernel returns the member-major layout. */
+int hm_swap01(hm_ctx* ctx, int64_t d0, int64_t d1, int64_t d2, const double* src, double* dst);
+
 #ifdef __cplusplus
 }
 #endif

@@ -327,3 +327,40 @@ def test_separable_prior_on_device():
     assert abs(F.var(0).mean() - 1) < 0.05
     c = np.mean(F[:, 10, 10] * F[:, 16, 10])   # 6 cells apart in x
     assert abs(c - np.exp(-3 * (6 * hx) ** 2 / r**2)) < 0.06
+
+
+# ---- sizes beyond the shared-memory workspaces (global-memory workspace path of the same kernels) ----------------------
+def test_les_more_observations_than_shared_memory_holds():
+    """ens_update0_loc with p = 240 > 165 active observations per parameter (a p x p tapered system does not fit 227 KB):
+    the local-analysis kernel runs from its global-memory workspace; same result as the reference algorithm."""
+    from historymatching_b200 import analysis as ha
+
+    kw, _, _ = _hm_case(40, 150, 240, seed=21)
+    rng = np.random.RandomState(2)
+    xy_prm = rng.rand(150, 2) * [2, 1]
+    xy_obs = np.tile(rng.rand(4, 2) * [2, 1], (60, 1))
+    taper = oa.bump(oa.pairwise_distances(xy_prm, xy_obs) / 2.5)      # wide taper: (almost) every observation active
+    assert (np.sqrt(taper) > 1e-2).sum(1).max() > 200
+    np.testing.assert_allclose(ha.ens_update0_loc(taper=taper, **kw), oa.ens_update0_loc(taper=taper, **kw), **TOL)
+
+
+def test_iles_notebook_ensemble_of_200():
+    """ILES at N = 200 members, p = 160 (BASELINE config 1 speaks of a ~200-member ensemble; SURVEY 8 size A "also N=200"):
+    3 N^2 + N p doubles = 1.2 MB per parameter, far beyond shared memory - global-memory workspace path."""
+    from historymatching_b200 import analysis as ha
+
+    N, M, p = 200, 60, 160
+    kw, _, H = _hm_case(N, M, p, seed=5)
+    kw.pop("obs_ens")
+    rng = np.random.RandomState(4)
+    xy_prm = rng.rand(M, 2) * [2, 1]
+    xy_obs = np.tile(rng.rand(4, 2) * [2, 1], (p // 4, 1))
+    taper = oa.bump(oa.pairwise_distances(xy_prm, xy_obs) / 1.2)
+
+    def fwd(X):
+        return np.tanh(X @ H)
+
+    E, st = ha.ILES(obs_ens=fwd, taper=taper, xStep=0.4, iMax=2, **kw)
+    E_ref, st_ref = oa.ILES(obs_ens=fwd, taper=taper, xStep=0.4, iMax=2, **kw)
+    np.testing.assert_allclose(E, E_ref, rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(np.array(st.Eo), np.array(st_ref.Eo), rtol=1e-7, atol=1e-9)
