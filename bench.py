@@ -217,6 +217,75 @@ def run_reference(args, wl, rank):
     print(json.dumps(line))
 
 
+# ---- the notebook-cell path: forward_model -> tools.utils.apply -> comp1 -> ResSim.sim ------------------------------
+def dropin_forward_bench(wl, reps=5):
+    """The call a notebook user makes (HistoryMatch.py:358-387, cells as in tests/test_notebook_flow_gpu.py): every member
+    deep-copies the model, sets its permeability and calls ``ResSim.sim``; the drop-in ``apply`` runs the members on
+    threads whose ``sim`` calls rendezvous into ONE ``hm_sim_batch_host`` (host buffers in, full saturation history
+    out).  Returns member*steps/s and the wall time per ensemble run, next to the same run through the array API."""
+    import copy
+
+    import historymatching_b200 as hmb
+
+    hmb.activate()
+    import TPFA_ResSim as simulator
+    from tools import geostat, utils
+    from tools.utils import apply
+
+    Nx, Ny, N, nTime, dt = wl["Nx"], wl["Ny"], wl["members"], wl["nTime"], 0.025
+    model = simulator.ResSim(Nx=Nx, Ny=Ny, Lx=2, Ly=1)
+    near01 = np.array([0.12, 0.87])
+    model.prd_xy = [[x, y] for y in model.Ly * near01 for x in model.Lx * near01]
+    model.inj_xy = [[model.Lx / 2, model.Ly / 2]]
+    model.inj_rates = [[1]]
+    model.prd_rates = np.ones((4, 1)) / 4
+    prod_inds = model.xy2ind(*model.prd_xy.T)
+    wsat0 = np.zeros(model.Nxy)
+    np.random.seed(1)
+    prior = np.clip(geostat.gaussian_fields(model.mesh, N, r=0.8), -2.2, 2.2)
+
+    def set_perm(model, log_perm_array):
+        p = (0.1 + np.exp(5 * log_perm_array)).reshape(model.shape)
+        model.K = np.stack([p, p])
+
+    def comp1(perm, wsat0=wsat0):
+        new_model = copy.deepcopy(model)
+        set_perm(new_model, perm)
+        wsats = new_model.sim(dt, nTime, wsat0, pbar=False)
+        prods = np.array([x[prod_inds] for x in wsats[1:]])
+        return wsats, prods
+
+    def forward_model(*args, **kwargs):
+        output = apply(comp1, *args, pbar=False, **kwargs)
+        return [np.asarray(y) for y in zip(*output)]
+
+    utils.nCPU = "auto"
+    forward_model(prior)  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        wsats, prods = forward_model(prior)
+    cells_s = (time.perf_counter() - t0) / reps
+    # the same ensemble through the array API with host buffers (no per-member Python objects)
+    from historymatching_b200.sim import GridSpec, run_ensemble
+
+    grid = GridSpec(Nx, Ny, 2.0, 1.0)
+    cells = np.concatenate([model.xy2ind(*model.inj_xy.T), prod_inds]).astype(np.int32)
+    rates = np.array([1.0, -0.25, -0.25, -0.25, -0.25])
+    K = 0.1 + np.exp(5 * prior)
+    run_ensemble(grid, K, cells, rates, wsat0, dt, nTime, obs_cell=prod_inds.astype(np.int32), history=True)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        res = run_ensemble(grid, K, cells, rates, wsat0, dt, nTime, obs_cell=prod_inds.astype(np.int32), history=True)
+    array_s = (time.perf_counter() - t0) / reps
+    assert np.array_equal(res.S_hist, wsats)
+    utils.nCPU = 1
+    return dict(value=N * nTime / cells_s, unit="member*steps/s", ms_per_ensemble_run=1e3 * cells_s,
+                array_api_host_buffers_ms=1e3 * array_s, members=N,
+                path="forward_model -> tools.utils.apply(comp1) -> copy.deepcopy(model), set_perm, ResSim.sim -> collector -> "
+                     "one hm_sim_batch_host; full (N, nTime+1, M) history returned to the cells",
+                d2h_bytes_per_run=int(8 * N * (nTime + 1) * Nx * Ny))
+
+
 # ---- update wall times + FP64 GEMM roofline (second half of the BASELINE metric) -----------------------
 def update_benchmarks(case, E0, Eo, noisy, pert, dec, cpu=True, reps=5):
     """ES / LES / IES-iteration wall times at the bench ensemble size (CUDA events, inputs resident) and the
@@ -587,6 +656,8 @@ def measure(args, wl, rank, world, local_rank, dev, steps, warmup, full):
         line["e2e"] = e2e
     if world == 1 and not args.no_update_bench:
         line["update"] = update_benchmarks(case, E0, Eo, noisy, pert, dec, cpu=not args.no_cpu_baseline)
+    if world == 1 and full and wl["Nx"] * wl["Ny"] <= 4096 and not args.no_e2e:
+        line["e2e_dropin"] = dropin_forward_bench(wl)  # the notebook-cell path (BASELINE configs 1, 2, 5)
     if not args.no_cpu_baseline and world == 1:
         v, cores, sample = cpu_forward_sample(wl, args.cpu_seconds)
         line["cpu_baseline"] = dict(value=v, unit="member*steps/s", cores=cores, kind="port", sample=sample)

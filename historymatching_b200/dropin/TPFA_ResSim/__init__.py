@@ -52,8 +52,11 @@ class ResSim(Grid2D, Plot2D):
                 raise ValueError("permeability must be positive")
         elif key in ("inj_xy", "prd_xy"):
             val = np.array(val, float).reshape((-1, 2))
+            cells = np.zeros(0, np.int32)
             if len(val):  # collocate with cell centres; raises outside the domain
-                val = self.ind2xy(self.xy2ind(*val.T)).T
+                cells = self.xy2ind(*val.T)
+                val = self.ind2xy(cells).T
+            object.__setattr__(self, "_" + key[:3] + "_cells", np.asarray(cells, np.int32))
         elif key in ("inj_rates", "prd_rates"):
             val = np.array(val, float)
             if val.ndim == 1:
@@ -61,6 +64,23 @@ class ResSim(Grid2D, Plot2D):
             if val.ndim != 2 or not np.all(np.isfinite(val)):
                 raise ValueError(f"{key} must be a finite (nWell, nTime|1) array")
         object.__setattr__(self, key, val)
+
+    def __deepcopy__(self, memo):
+        """``copy.deepcopy(model)`` is what every member's forward run starts with (``HistoryMatch.py:360``,
+        ``Optimise.py:133``): copy the arrays directly instead of walking the object graph (~10x faster)."""
+        new = object.__new__(type(self))
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if isinstance(v, np.ndarray):
+                v = v.copy()
+            elif isinstance(v, dict) and all(isinstance(x, np.ndarray) for x in v.values()):
+                v = {kk: x.copy() for kk, x in v.items()}
+            elif not isinstance(v, (int, float, str, bool, type(None))):
+                import copy
+
+                v = copy.deepcopy(v, memo)
+            object.__setattr__(new, k, v)
+        return new
 
     @property
     def nInj(self):
@@ -83,9 +103,9 @@ class ResSim(Grid2D, Plot2D):
             r = np.broadcast_to(r, (len(r), nSteps)) if r.shape[1] == 1 else r[:, :nSteps]
             rates.append(sign * r)
         q = np.concatenate(rates).T  # (nSteps, nW)
-        if not np.allclose(q.sum(1), 0.0):
+        if np.abs(q.sum(1)).max(initial=0.0) > 1e-8:  # np.allclose(q.sum(1), 0) without its overhead
             raise ValueError("total injection must equal total production at every time step")
-        cells = np.concatenate([self.xy2ind(*self.inj_xy.T), self.xy2ind(*self.prd_xy.T)]).astype(np.int32)
+        cells = np.concatenate([self._inj_cells, self._prd_cells])  # collocated when the wells were set
         self.actual_rates = {"inj": np.array(rates[0]), "prd": -np.array(rates[1])}
         return np.ascontiguousarray(q), cells
 

@@ -181,13 +181,30 @@ def apply(fun, *args, pbar=True, **kwargs):
     return output
 
 
+_pool = None
+_pool_lock = threading.Lock()
+
+
+def _member_pool():
+    """Persistent worker threads for the members of a batch (creating 40 threads per ensemble run costs more than the
+    20 x 20 forward run itself).  Every member of a chunk needs its own thread: a member blocks inside ``ResSim.sim``
+    until the whole chunk has arrived at the collector."""
+    global _pool
+    from concurrent.futures import ThreadPoolExecutor
+
+    with _pool_lock:
+        if _pool is None or _pool._max_workers < max_batch:
+            _pool = ThreadPoolExecutor(max_workers=max_batch, thread_name_prefix="hm-member")
+        return _pool
+
+
 def _batched_map(_fun, inputs, pbar):
     """Run the members on threads; their ``ResSim.sim`` calls rendezvous into batched GPU runs."""
     from TPFA_ResSim import Collector
 
     output = [None] * len(inputs)
     errors = [None] * len(inputs)
-    lock = threading.Lock()
+    pool = _member_pool()
     for lo in range(0, len(inputs), max_batch):
         idx = range(lo, min(lo + max_batch, len(inputs)))
         collector = Collector(len(idx))
@@ -201,14 +218,10 @@ def _batched_map(_fun, inputs, pbar):
             finally:
                 collector.detach()
                 collector.finish()
-                with lock:
-                    pbar.update()
 
-        threads = [threading.Thread(target=work, args=(i,), daemon=True) for i in idx]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
+        for f in [pool.submit(work, i) for i in idx]:
+            f.result()
+            pbar.update()
         for e in errors:
             if e is not None:
                 raise e
