@@ -42,6 +42,7 @@ class SimDesc(C.Structure):
         ("cg_rtol", C.c_double), ("cg_max_iter", C.c_int32),
         ("chunk_members", C.c_int32), ("precond", C.c_int32), ("mg_switch_iters", C.c_int32), ("sat_block", C.c_int32), ("hist_stride", C.c_int32), ("warm_start", C.c_int32),
         ("tb_cluster_rows", C.c_int32), ("tb_halo", C.c_int32),
+        ("K_transform", C.c_int32), ("K_a", C.c_double), ("K_b", C.c_double),
     ]
 
 

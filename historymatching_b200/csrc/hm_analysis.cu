@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256)
 k_local_analysis(int64_t M, int p, double nm1, const double* __restrict__ A,
                  const double* __restrict__ taper, double* __restrict__ B, int64_t ldB,
                  int* __restrict__ fail, double* gws, size_t gws_stride) {
-    // Workspace: dynamic shared memory where the tapered p x p system fits (p <= 165), otherwise this CTA's slab of
+    // Workspace: dynamic shared memory where the packed triangle of the tapered p x p system fits (p <= 236), otherwise this CTA's slab of
     // a global-memory workspace (L1 / L2 resident; the CTA barrier orders its accesses) - same algorithm, no size limit.
     extern __shared__ double sm_dyn[];
     double* sm = gws ? gws + blockIdx.x * gws_stride : sm_dyn;
@@ -134,10 +134,11 @@ k_local_analysis(int64_t M, int p, double nm1, const double* __restrict__ A,
     double* c = sm;           // [p] sqrt(taper) of active obs
     double* rhs = sm + p;     // [p]
     int* idx = (int*)(sm + 2 * p);  // [p] active obs indices
-    double* L = sm + 2 * p + (p + 1) / 2;  // [pi][pi] row-major, lower triangle
+    double* L = sm + 2 * p + (p + 1) / 2;  // lower triangle, packed by rows: (a, b <= a) at a (a + 1) / 2 + b
     __shared__ int s_n;
     __shared__ int s_fail;
     const int tid = threadIdx.x, nt = blockDim.x;
+    auto tri = [](int a, int b) { return a * (a + 1) / 2 + b; };
 
     // ordered compaction of the active set (ascending j, like boolean indexing)
     if (tid == 0) {
@@ -158,38 +159,38 @@ k_local_analysis(int64_t M, int p, double nm1, const double* __restrict__ A,
     for (int a = tid; a < n; a += nt) rhs[a] = c[a] * B[(int64_t)idx[a] * ldB + i];
     for (int e = tid; e < n * n; e += nt) {
         const int a = e / n, b = e % n;
-        if (b <= a) L[a * n + b] = c[a] * c[b] * A[(int64_t)idx[a] * p + idx[b]] + (a == b ? nm1 : 0.0);
+        if (b <= a) L[tri(a, b)] = c[a] * c[b] * A[(int64_t)idx[a] * p + idx[b]] + (a == b ? nm1 : 0.0);
     }
     __syncthreads();
     // right-looking Cholesky
     for (int k = 0; k < n; ++k) {
-        const double dkk = L[k * n + k];
+        const double dkk = L[tri(k, k)];
         if (tid == 0 && !(dkk > 0.0)) s_fail = 1;
         const double d = sqrt(dkk);
         __syncthreads();
-        for (int a = k + tid; a < n; a += nt) L[a * n + k] = (a == k) ? d : L[a * n + k] / d;
+        for (int a = k + tid; a < n; a += nt) L[tri(a, k)] = (a == k) ? d : L[tri(a, k)] / d;
         __syncthreads();
         const int rem = n - k - 1;
         for (int e = tid; e < rem * rem; e += nt) {
             const int a = k + 1 + e / rem, b = k + 1 + e % rem;
-            if (b <= a) L[a * n + b] -= L[a * n + k] * L[b * n + k];
+            if (b <= a) L[tri(a, b)] -= L[tri(a, k)] * L[tri(b, k)];
         }
         __syncthreads();
     }
     // forward / backward substitution (warp 0; columns processed in order)
     if (tid < 32) {
         for (int k = 0; k < n; ++k) {
-            const double yk = rhs[k] / L[k * n + k];
+            const double yk = rhs[k] / L[tri(k, k)];
             __syncwarp();
             if (tid == 0) rhs[k] = yk;
-            for (int a = k + 1 + tid; a < n; a += 32) rhs[a] -= L[a * n + k] * yk;
+            for (int a = k + 1 + tid; a < n; a += 32) rhs[a] -= L[tri(a, k)] * yk;
             __syncwarp();
         }
         for (int k = n - 1; k >= 0; --k) {
-            const double wk = rhs[k] / L[k * n + k];
+            const double wk = rhs[k] / L[tri(k, k)];
             __syncwarp();
             if (tid == 0) rhs[k] = wk;
-            for (int a = tid; a < k; a += 32) rhs[a] -= L[k * n + a] * wk;
+            for (int a = tid; a < k; a += 32) rhs[a] -= L[tri(k, a)] * wk;
             __syncwarp();
         }
     }
@@ -526,7 +527,7 @@ extern "C" int hm_les_update(hm_ctx* ctx, int64_t N, int64_t M, int64_t p, doubl
     HM_REQUIRE(ctx && E && Eo && obs && perturbs && decorr && taper, "null pointer");
     HM_REQUIRE(N > 1 && M > 0 && p > 0 && ldE >= M, "shape");
     HM_CUDA(cudaSetDevice(ctx->device));
-    size_t smem = ((size_t)2 * p + (p + 1) / 2 + (size_t)p * p) * sizeof(double);
+    size_t smem = ((size_t)2 * p + (p + 1) / 2 + (size_t)p * (p + 1) / 2) * sizeof(double);  // packed lower triangle: two CTAs per SM at p = 160
     double *S, *D, *A, *B;
     int* fail;
     HM_CHECK(whiten(ctx, N, p, Eo, obs, perturbs, decorr, &S, &D));
@@ -674,31 +675,61 @@ __global__ void k_corr_prep(int64_t N, int64_t q, const double* __restrict__ b, 
     sb[t] = sqrt(v / (double)(N - 1));
 }
 
-__global__ void __launch_bounds__(128)
+// A block owns 32 adjacent columns; its 8 warps split the ensemble rows (row i goes to warp i mod 8), so 8 x as many
+// loads are in flight as with one thread per column, and the second pass over the block's 32-column slab comes from L2.
+// Partial sums are combined through shared memory in a fixed order (deterministic).
+constexpr int kCorrSlices = 8;
+
+__global__ void __launch_bounds__(32 * kCorrSlices)
 k_corr_fields(int64_t N, int64_t M, int64_t q, int64_t t0, const double* __restrict__ a, int64_t lda,
               const double* __restrict__ Bc, const double* __restrict__ sb, double* __restrict__ out,
               int corr) {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= M) return;
+    __shared__ double red[kCorrSlices][kCorrQ + 1][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int64_t j = (int64_t)blockIdx.x * 32 + cx;
+    const bool live = j < M;
     const int nq = (int)min((int64_t)kCorrQ, q - t0);
+    const double* col = a + (live ? j : 0);
+    double s0 = 0.0, s1 = 0.0;
+    int64_t i = ry;
+    for (; i + kCorrSlices < N; i += 2 * kCorrSlices) {
+        s0 += col[i * lda];
+        s1 += col[(i + kCorrSlices) * lda];
+    }
+    if (i < N) s0 += col[i * lda];
+    red[ry][0][cx] = s0 + s1;
+    __syncthreads();
     double s = 0.0;
-    for (int64_t i = 0; i < N; ++i) s += a[i * lda + j];
+#pragma unroll
+    for (int r = 0; r < kCorrSlices; ++r) s += red[r][0][cx];
     const double mu = s / (double)N;
+    __syncthreads();
     double v = 0.0, acc[kCorrQ];
 #pragma unroll
     for (int t = 0; t < kCorrQ; ++t) acc[t] = 0.0;
-    for (int64_t i = 0; i < N; ++i) {
-        const double d = a[i * lda + j] - mu;
+    for (i = ry; i < N; i += kCorrSlices) {
+        const double d = col[i * lda] - mu;
         v = fma(d, d, v);
 #pragma unroll
         for (int t = 0; t < kCorrQ; ++t)
             if (t < nq) acc[t] = fma(d, __ldg(Bc + i * q + t0 + t), acc[t]);
     }
+    red[ry][0][cx] = v;
+#pragma unroll
+    for (int t = 0; t < kCorrQ; ++t) red[ry][t + 1][cx] = acc[t];
+    __syncthreads();
+    if (ry != 0 || !live) return;
+    v = 0.0;
+#pragma unroll
+    for (int r = 0; r < kCorrSlices; ++r) v += red[r][0][cx];
     const double sa = sqrt(v / (double)(N - 1));
 #pragma unroll
     for (int t = 0; t < kCorrQ; ++t) {
         if (t < nq) {
-            double c = acc[t] / (double)(N - 1);
+            double c = 0.0;
+#pragma unroll
+            for (int r = 0; r < kCorrSlices; ++r) c += red[r][t + 1][cx];
+            c /= (double)(N - 1);
             if (corr) {
                 c = c / sa / sb[t0 + t];
                 if (!isnan(c)) c = fmin(fmax(c, -999.0), 999.0);  // 0/0 stays NaN, as with np.clip
@@ -721,7 +752,7 @@ extern "C" int hm_corr(hm_ctx* ctx, int64_t N, int64_t M, int64_t q, const doubl
     HM_CHECK(ctx->ws.get("an.corr_sb", (size_t)q, &sb));
     k_corr_prep<<<(unsigned)((q + 63) / 64), 64, 0, ctx->stream>>>(N, q, b, ldb, Bc, sb);
     for (int64_t t0 = 0; t0 < q; t0 += kCorrQ)
-        k_corr_fields<<<(unsigned)((M + 127) / 128), 128, 0, ctx->stream>>>(N, M, q, t0, a, lda, Bc, sb, out, corr);
+        k_corr_fields<<<(unsigned)((M + 31) / 32), 32 * kCorrSlices, 0, ctx->stream>>>(N, M, q, t0, a, lda, Bc, sb, out, corr);
     ctx->launches += 1 + (q + kCorrQ - 1) / kCorrQ;
     HM_CUDA(cudaGetLastError());
     return HM_OK;

@@ -65,8 +65,8 @@ k_tpfa_setup(Geo g, const double* __restrict__ S, const double* __restrict__ K, 
         if (row >= 0 && row < g.Nx) {
             const int c = row * g.Ny + col;
             const double mt = total_mobility(Sm[c], g);
-            lx = 1.0 / (mt * Kx[c]);
-            ly = 1.0 / (mt * Ky[c]);
+            lx = 1.0 / (mt * perm_value(g, Kx[c]));
+            ly = 1.0 / (mt * perm_value(g, Ky[c]));
         }
         Lx[i] = lx;
         Ly[i] = ly;
@@ -81,7 +81,7 @@ k_tpfa_setup(Geo g, const double* __restrict__ S, const double* __restrict__ K, 
         const double tyh = col < g.Ny - 1 ? g.cy / (Ly[li] + Ly[li + 1]) : 0.0;
         double d = tyl + tyh + txl + txh;
         if (c == 0) {  // pin of the singular Neumann problem: A[0,0] += Kx[0]+Ky[0]
-            const double pv = Kx[0] + Ky[0];
+            const double pv = perm_value(g, Kx[0]) + perm_value(g, Ky[0]);
             d += pv;
             pin[m] = pv;
         }
@@ -713,6 +713,9 @@ int sim_chunk(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
     g.vo = d.vo;
     g.swc = d.swc;
     g.sor = d.sor;
+    g.k_transform = d.K_transform;
+    g.k_a = d.K_a;
+    g.k_b = d.K_b;
     Fluid fl;
     fl.inv_range = 1.0 / (1.0 - d.swc - d.sor);
     fl.swc_ir = d.swc * fl.inv_range;
@@ -969,6 +972,7 @@ int validate(const hm_sim_desc& d) {
     HM_REQUIRE(d.n_wells == 0 || (d.well_cell && d.well_rate), "well arrays");
     HM_REQUIRE(d.n_steps >= 0 && d.dt > 0, "dt, n_steps");
     HM_REQUIRE(d.n_obs == 0 || d.obs_cell, "obs_cell");
+    HM_REQUIRE(d.K_transform == 0 || d.K_transform == 1, "K_transform: 0 = permeability, 1 = K_a + exp(K_b x)");
     HM_REQUIRE(d.Ny <= 1024, "Ny <= 1024 (row tiles of at least two grid rows must fit 2048 cells)");
     HM_REQUIRE(d.precond >= 0 && d.precond <= 4,
                "precond: 0 = multigrid V-cycle (FP32 cycle, FP64 fallback), 1 = Jacobi, 2 = FP64 W-cycle, 3 = FP32 V-cycle, "

@@ -17,7 +17,12 @@ struct Geo {
     double cy;   // 2*hx/hy
     double h2;   // hx*hy
     double vw, vo, swc, sor;
+    int k_transform;  // hm_sim_desc.K_transform: 1 = the K array holds x, permeability = k_a + exp(k_b x)
+    double k_a, k_b;
 };
+
+// permeability of a cell from the caller's K array (perm_transf of the notebooks, HistoryMatch.py:137-138, when asked for)
+__device__ __forceinline__ double perm_value(const Geo& g, double k) { return g.k_transform ? g.k_a + exp(g.k_b * k) : k; }
 
 // Saturation history layout (hm_sim_desc.hist_stride): row 0 = S0, then the states after steps k, 2k, ... and after
 // the last step.  hist_row(step_done) = the row of the state after `step_done` steps, or -1 if it is not stored.

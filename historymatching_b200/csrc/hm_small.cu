@@ -292,7 +292,7 @@ k_sim_small(const __grid_constant__ SmallArgs a) {
 
     const double* Kx = a.K + (int64_t)m * a.K_ms;
     const double* Ky = Kx + a.K_cs;
-    const double pinv = Kx[0] + Ky[0];  // pin of the singular Neumann problem: A[0,0] += Kx[0] + Ky[0]
+    const double pinv = perm_value(g, Kx[0]) + perm_value(g, Ky[0]);  // pin of the singular Neumann problem: A[0,0] += Kx[0] + Ky[0]
     for (int e = tid; e < M; e += NT) S[e] = a.S0[(int64_t)m * a.S0_ms + e];
     if (a.S_hist)
         for (int e = tid; e < M; e += NT)
@@ -305,8 +305,8 @@ k_sim_small(const __grid_constant__ SmallArgs a) {
         // ---- transmissibilities (Appendix A.2); 1/mobility staged in Pd / AP ----------------------------
         for (int e = tid; e < M; e += NT) {
             const double mob = total_mobility(S[e], g);
-            Pd[e] = 1.0 / (mob * Kx[e]);
-            AP[e] = 1.0 / (mob * Ky[e]);
+            Pd[e] = 1.0 / (mob * perm_value(g, Kx[e]));
+            AP[e] = 1.0 / (mob * perm_value(g, Ky[e]));
         }
         __syncthreads();
         double txl[kSmallPer], tyl[kSmallPer], dv[kSmallPer];
@@ -567,6 +567,9 @@ int sim_small(hm_ctx* ctx, const hm_sim_desc& d, int m0, int nm) {
     g.vo = d.vo;
     g.swc = d.swc;
     g.sor = d.sor;
+    g.k_transform = d.K_transform;
+    g.k_a = d.K_a;
+    g.k_b = d.K_b;
     a.fl.inv_range = 1.0 / (1.0 - d.swc - d.sor);
     a.fl.swc_ir = d.swc * a.fl.inv_range;
     a.fl.mr = d.vw / d.vo;

@@ -156,7 +156,7 @@ def _run_ensemble_one(grid: GridSpec, K, well_cell, well_rate, S0, dt, n_steps, 
                       _alloc_only=False,
                  obs_cell=None, por=None, history=False, pressure=False, want_substeps=False,
                  cg_rtol=0.0, cg_max_iter=0, chunk_members=0, precond=0, mg_switch_iters=0, sat_block=0, warm_start=0,
-                 tb_cluster_rows=0, tb_halo=0, ctx=None) -> SimResult:
+                 tb_cluster_rows=0, tb_halo=0, k_transform=None, ctx=None) -> SimResult:
     """Run ``n_steps`` of the simulator for every ensemble member.
 
     K          (M,) shared isotropic; (N,M) isotropic; (N,2,M) anisotropic (Kx, Ky);
@@ -165,6 +165,8 @@ def _run_ensemble_one(grid: GridSpec, K, well_cell, well_rate, S0, dt, n_steps, 
     well_rate  signed rates (+inj, -prd): (nW,) constant & shared; (nT,nW) shared
                schedule; (N,1,nW) / (N,nT,nW) per member
     S0         (M,) shared or (N,M)
+    k_transform  ``(a, b)``: ``K`` holds the notebooks' log-permeability parameter ``x`` and the permeability is
+               ``a + exp(b x)`` (``perm_transf``, ``HistoryMatch.py:137-138``: ``(0.1, 5)``), evaluated inside the kernels
     history    True: ``S_hist (N, n_steps+1, M)`` (row 0 = S0, the reference's ``ResSim.sim`` output);
                an int k > 1: every k-th step and the last one, ``(N, 1 + ceil(n_steps/k), M)``
     """
@@ -282,6 +284,8 @@ def _run_ensemble_one(grid: GridSpec, K, well_cell, well_rate, S0, dt, n_steps, 
     d.hist_stride = hist_stride
     d.warm_start = int(warm_start)
     d.tb_cluster_rows, d.tb_halo = int(tb_cluster_rows), int(tb_halo)
+    if k_transform is not None:
+        d.K_transform, d.K_a, d.K_b = 1, float(k_transform[0]), float(k_transform[1])
 
     if use_torch:
         ctx = ctx or _lib.Context.get(dev.index if dev.index is not None else 0)

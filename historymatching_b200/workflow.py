@@ -81,7 +81,8 @@ class HistoryMatchCase:
         Returns ``(obs (N, nTime*nPrd), SimResult)``; tensors stay on the device for CUDA input.
         """
         is_t = type(logperm).__module__.startswith("torch")
-        K = self.perm_transf(logperm)
+        K = logperm  # perm_transf (0.1 + exp(5 x)) is evaluated where the transmissibilities are built
+        kw.setdefault("k_transform", (0.1, 5.0))
         if S0 is None:
             S0 = np.zeros(self.grid.M)
             if is_t:

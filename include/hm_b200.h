@@ -129,6 +129,11 @@ typedef struct hm_sim_desc {
                             * <= 0: chosen from the grid and the device's cluster occupancy */
     int32_t tb_halo;       /* the same kernel: sub-steps per round (= overlap rows of neighbouring row strips) when a member
                             * does not fit one cluster; <= 0: automatic */
+    int32_t K_transform;   /* 0: K holds permeabilities.  1: K holds the notebook's log-permeability parameter x and the
+                            * permeability is K_a + exp(K_b x) - perm_transf, HistoryMatch.py:137-138 (0.1 + exp(5 x)) -
+                            * evaluated where the transmissibilities are built, so that an ensemble update can hand its
+                            * parameter matrix to the forward run as it is */
+    double K_a, K_b;
 } hm_sim_desc;
 
 /* statistics of the last hm_sim_batch on this ctx (host side) */

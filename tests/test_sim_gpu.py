@@ -351,3 +351,24 @@ def test_buckley_leverett_known_answer(sat_block):
     assert np.abs(S[:, 0] - exact).mean() < 0.009                           # first-order upwind at h = 1/200
     assert abs(x[np.argmax(S[:, 0] < 0.35)] - v_shock * T) < 0.012
     assert abs(S[:, 0].sum() * hx - T) < 1e-10                              # injected volume
+
+
+@pytest.mark.parametrize("Nx,Ny", [(20, 20), (64, 64)])
+def test_perm_transf_inside_the_kernels(Nx, Ny):
+    """hm_sim_desc.K_transform: the forward run takes the log-permeability parameter x and evaluates the notebook's
+    perm_transf 0.1 + exp(5 x) (HistoryMatch.py:137-138) where the transmissibilities are built (fused and streamed
+    path); same result as handing it the transformed field (exp differs from numpy's in the last bit at most)."""
+    from historymatching_b200.sim import run_ensemble
+
+    m, grid, logk, cells, rates, prd = _setup(Nx, Ny, 3, seed=8)
+    args = (cells, rates, np.zeros(grid.M), 0.025, 3)
+    a = run_ensemble(grid, orr.perm_transf(logk), *args, obs_cell=prd, pressure=True)
+    b = run_ensemble(grid, logk, *args, obs_cell=prd, pressure=True, k_transform=(0.1, 5.0))
+    assert not b.status.any()
+    # K differs in the last bit, each pressure solve is accurate to the CG tolerance: the stated parity tolerance applies
+    np.testing.assert_allclose(b.S_last, a.S_last, rtol=0, atol=SAT_TOL)
+    np.testing.assert_allclose(b.obs, a.obs, rtol=0, atol=SAT_TOL)
+    np.testing.assert_allclose(b.P_last, a.P_last, rtol=0, atol=1e-8 * np.abs(a.P_last).max())
+    # and against the oracle (which transforms on the host)
+    wsats, _ = _oracle(m, logk, 0.025, 3, np.zeros(grid.M), prd)
+    np.testing.assert_allclose(b.S_last, wsats[:, -1], rtol=0, atol=SAT_TOL)
