@@ -156,7 +156,14 @@ __device__ __forceinline__ double frac_flow_loop(double s, const Fluid& f) {
     const double a = se * se;
     return fast_div_h(a, UNIT ? fma(t, t, a) : fma(f.mr * t, t, a));
 }
-
+// the same with the constant 1 passed in (a register the caller obtained from a volatile asm: orders the evaluation behind it)
+template <bool UNIT>
+__device__ __forceinline__ double frac_flow_one(double s, const Fluid& f, double one) {
+    const double se = UNIT ? s : fma(s, f.inv_range, -f.swc_ir);
+    const double t = one - se;
+    const double a = se * se;
+    return fast_div_h(a, UNIT ? fma(t, t, a) : fma(f.mr * t, t, a));
+}
 
 // Vector access helpers: N consecutive elements at a 16-byte aligned address as 128-bit transactions.
 template <int N, typename U>

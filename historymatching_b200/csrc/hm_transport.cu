@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_sat_tb(TbArgs a, Fluid fl, We
     __shared__ int ntss[2];
     __shared__ int wl_tid[kMaxWells], wl_slot[kMaxWells];
     __shared__ double wl_neg[kMaxWells], wl_pos[kMaxWells];
-    __shared__ int wl_n;
+    __shared__ int wl_n[2];
     __shared__ __align__(8) unsigned long long bars[4];  // halo exchange (per fw buffer), staging, CTA split barrier
 
     cg::cluster_group cluster = cg::this_cluster();
@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_sat_tb(TbArgs a, Fluid fl, We
     // of the patch (r = 0..4), wy[r][j]: face between columns j-1 and j (j = 0..2).
     double S[4][2], wx[5][2], wy[4][3];
     int wcode = -1, nwl = 0;
+    if (tid < 2) wl_n[tid] = 0;  // visible behind the barrier / cluster barrier below
 
     // Hazards (as in k_sat_cluster): the threads that read a halo row / column filled by a neighbour are exactly the
     // threads that send the matching edge row / column to that neighbour, and a sender has waited for the complete
@@ -197,10 +198,31 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_sat_tb(TbArgs a, Fluid fl, We
     auto substep = [&](double* __restrict__ fw, uint32_t mybar, uint32_t xa, uint32_t xb, uint32_t ya, uint32_t yb,
                        int parity) {
         double f[4][2];
+        if constexpr (NQ <= 2) {
+            // every warp owns an edge row: the two candidate edge rows first, sent at once, so that the neighbouring tile
+            // has them as early as possible; the other rows depend (through `one`) on a volatile asm behind the sends,
+            // which keeps the compiler from hoisting them above
+            f[0][0] = frac_flow_loop<UNIT>(S[0][0], fl);
+            f[0][1] = frac_flow_loop<UNIT>(S[0][1], fl);
+            f[3][0] = frac_flow_loop<UNIT>(S[3][0], fl);
+            f[3][1] = frac_flow_loop<UNIT>(S[3][1], fl);
+            if (sX) {
+                st_async_f64(xa, sUp ? f[0][0] : f[3][0], xb);
+                st_async_f64(xa + 8u * OO, sUp ? f[0][1] : f[3][1], xb);
+            }
+            double one;
+            asm volatile("mov.f64 %0, 0d3FF0000000000000;" : "=d"(one));
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            f[r][0] = frac_flow_loop<UNIT>(S[r][0], fl);
-            f[r][1] = frac_flow_loop<UNIT>(S[r][1], fl);
+            for (int r = 1; r < 3; ++r) {
+                f[r][0] = frac_flow_one<UNIT>(S[r][0], fl, one);
+                f[r][1] = frac_flow_one<UNIT>(S[r][1], fl, one);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                f[r][0] = frac_flow_loop<UNIT>(S[r][0], fl);
+                f[r][1] = frac_flow_loop<UNIT>(S[r][1], fl);
+            }
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -213,7 +235,7 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_sat_tb(TbArgs a, Fluid fl, We
         if (!(a.probe & 4)) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ctabar) : "memory");
         // edge rows / columns into the neighbours' halo slots.  (STAS cannot be predicated: one branch per direction,
         // the row direction is warp-uniform, the column direction is taken by one lane per warp.)
-        if (sX) {
+        if (NQ > 2 && sX) {
             st_async_f64(xa, sUp ? f[0][0] : f[3][0], xb);
             st_async_f64(xa + 8u * OO, sUp ? f[0][1] : f[3][1], xb);
         }
@@ -294,10 +316,30 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_sat_tb(TbArgs a, Fluid fl, We
                 S[r][1] = fma(-wy[r][2], upwind(wy[r][2], f[r][1], fr_), S[r][1]);
             }
         };
-        if (needWait) halo_wait();
-        top();
-        bottom();
-        sides();
+        if constexpr (NQ <= 2) {
+            // Tiles of two row groups (W = 512): EVERY warp owns an edge row and waits for a halo row each sub-step.  First the
+            // faces whose neighbour lives in this CTA, then - behind the wait - the two that face another tile of the cluster:
+            // the DSMEM latency overlaps with 10 of the 12 faces (measured at 512^2: 488 -> 462 ms per step; on taller tiles,
+            // where only 4 of 16 warps wait, the extra branches cost more than they hide: 15.6 -> 17.3 ms at 128^2).
+            bool waited = false;
+            if (sLf || sRt) {  // a halo column is needed by sides()
+                halo_wait();
+                waited = true;
+            }
+            sides();
+            if (!sUp) top();
+            if (!sDn) bottom();
+            if (sX) {
+                if (!waited) halo_wait();
+                if (sUp) top();
+                if (sDn) bottom();
+            }
+        } else {
+            if (needWait) halo_wait();
+            top();
+            bottom();
+            sides();
+        }
     };
     double* const fwa = fb0 + tb;
     double* const fwb = fb1 + tb;
@@ -330,6 +372,23 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_sat_tb(TbArgs a, Fluid fl, We
         const double dtx = dts / a.h2;
         const int* wc = wcs[slot];
         const double* wr = wrs[slot];
+        // wells of this tile: (owning thread, cell slot in its patch, dtx * min(q,0), dtx * max(q,0)); built by warp 1 while
+        // the other warps turn the staged tile into registers
+        for (int i = tid - 32; i >= 0 && i < w.n; i += kTbThreads) {
+            const int cc = wc[i];
+            bool first = true;
+            for (int k = 0; k < i; ++k) first = first && (wc[k] != cc);
+            if (!first) continue;
+            const int gr = cc / a.Ny, gc = cc - gr * a.Ny;
+            const int lr = gr - (s0 + cxi * R), lc = gc - col0;
+            if (lr < 0 || lr >= R || lc < 0 || lc >= W) continue;
+            const double qs = cell_source(cc, w.n, wc, wr) * dtx;
+            const int e = atomicAdd(&wl_n[slot], 1);
+            wl_tid[e] = (lr >> 2) * H + (lc >> 1);
+            wl_slot[e] = (lr & 3) * 2 + (lc & 1);
+            wl_neg[e] = fmin(qs, 0.0);
+            wl_pos[e] = fmax(qs, 0.0);
+        }
         mbar_wait(ldbar, item & 1);
         stamp(item, 1);
 #pragma unroll
@@ -356,27 +415,10 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_sat_tb(TbArgs a, Fluid fl, We
                 wy[r][2] = dtx * yp[2];  // column Ny is column 0 of the next row: a zero face
             }
         }
-        if (tid == 0) wl_n = 0;
-        __syncthreads();  // the staging buffers are free, the well list of the previous item is no longer read
+        __syncthreads();  // the staging buffers are free; the well list (built by warp 1 meanwhile) is complete
         if (work + nClusters < nWork) prefetch(work + nClusters, slot ^ 1);  // overlaps this item's sub-steps
-        // wells of this tile: (owning thread, cell slot in its patch, dtx * min(q,0), dtx * max(q,0))
-        for (int i = tid; i < w.n; i += kTbThreads) {
-            const int cc = wc[i];
-            bool first = true;
-            for (int k = 0; k < i; ++k) first = first && (wc[k] != cc);
-            if (!first) continue;
-            const int gr = cc / a.Ny, gc = cc - gr * a.Ny;
-            const int lr = gr - (s0 + cxi * R), lc = gc - col0;
-            if (lr < 0 || lr >= R || lc < 0 || lc >= W) continue;
-            const double qs = cell_source(cc, w.n, wc, wr) * dtx;
-            const int e = atomicAdd(&wl_n, 1);
-            wl_tid[e] = (lr >> 2) * H + (lc >> 1);
-            wl_slot[e] = (lr & 3) * 2 + (lc & 1);
-            wl_neg[e] = fmin(qs, 0.0);
-            wl_pos[e] = fmax(qs, 0.0);
-        }
-        __syncthreads();
-        nwl = wl_n;
+        if (tid == 0) wl_n[slot ^ 1] = 0;  // the next item's counter: last read before this item's first barrier
+        nwl = wl_n[slot];
         // this thread's first entry of the list, its cell slot and "the patch holds further wells", packed into one
         // register (-1: the patch holds no well)
         wcode = -1;
