@@ -450,8 +450,11 @@ def measure(args, wl, rank, world, local_rank, dev, steps, warmup, full):
             print(f"[bench +{time.perf_counter() - t_start:7.1f}s] {msg}", file=sys.stderr, flush=True)
 
     def one_pass(E):
+        f0 = torch.cuda.Event(enable_timing=True)
+        f0.record()
         Eo, res = case.forward(E, want_substeps=True, sat_block=args.sat_block, precond=args.precond, lanes=args.lanes)
         last["res"] = res
+        last["fwd0"] = f0
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
         if world > 1:
@@ -484,7 +487,7 @@ def measure(args, wl, rank, world, local_rank, dev, steps, warmup, full):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     phase = dict(setup=0.0, cg=0.0, flux=0.0, saturation=0.0, obs=0.0)
-    upd_ms, cg_member_iters, sat_member_substeps = 0.0, 0, 0
+    upd_ms, fwd_ms, cg_member_iters, sat_member_substeps = 0.0, 0.0, 0, 0
     stats_acc = dict(cg_kernel_launches=0, sat_kernel_launches=0, mg_fp64_fallbacks=0, kernel_launches=0, sat_cell_updates=0)
     torch.cuda.nvtx.range_push("timed")  # lets ncu select the timed region (--nvtx --nvtx-include "timed/")
     for _ in range(args.steps):
@@ -494,6 +497,7 @@ def measure(args, wl, rank, world, local_rank, dev, steps, warmup, full):
         for k in phase:
             phase[k] += res.stats["phase_ms"][k]
         upd_ms += last["upd"][0].elapsed_time(last["upd"][1])
+        fwd_ms += last["fwd0"].elapsed_time(last["upd"][0])
         cg_member_iters += int(res.cg_iters.sum())
         sat_member_substeps += int(res.substeps.sum())
         for k in stats_acc:
@@ -645,7 +649,7 @@ def measure(args, wl, rank, world, local_rank, dev, steps, warmup, full):
                     nTime=wl["nTime"], p=p, update="ES (one ES-MDA pass, alpha=4)",
                     l2="inputs larger than L2 (working set %.1f GB per GPU)" % (13 * N_loc * M * 8 / 1e9),
                     parallelism=f"members sharded x{world}", lanes_per_gpu=int(last["res"].stats.get("lanes", 1))),
-        update_ms=upd_ms / args.steps,
+        update_ms=upd_ms / args.steps, forward_ms=fwd_ms / args.steps,
         phases_ms_per_step={k: v / args.steps for k, v in phase.items()},
         secondary_kernel=dict(kernel=other, achieved=(ob / (ot * 1e-3) / 1e9 if ot > 0 else 0.0), unit="GB/s"),
         members_failed=bad, gpu_launches=int(launches), clocks=sampler.summary(), roofline=roofline,
