@@ -75,12 +75,13 @@ def run_ensemble(grid: GridSpec, K, well_cell, well_rate, S0, dt, n_steps, *, n_
     """Run ``n_steps`` of the simulator for every ensemble member (see ``_run_ensemble_one`` for the arguments).
 
     ``lanes = L > 1`` (device path only): the members are split into L contiguous shares that run concurrently from L
-    host threads, each with its own library context (workspace) and CUDA stream.  The cluster transport kernel can
-    occupy 120 of the 148 SMs and leaves HBM idle, the pressure solve is HBM bound: a second lane fills the gaps
-    (measured at 128^2 x 1024 members: 1.04x with 2 lanes, 1.06x with 4; results bit-identical,
-    profiles/two_lanes_r1.txt).  ``lanes = 0``: 2 where the cluster transport kernel runs and the ensemble has at
-    least 256 members, else 1.  ``stats`` are summed over the lanes (phase times therefore add up to more than the
-    wall time).
+    host threads, each with its own library context (workspace) and CUDA stream.  The on-chip transport kernels are
+    bound by the FP64 pipe and leave HBM idle, the pressure solve is HBM / latency bound and leaves the FP64 pipe idle:
+    with two lanes one share's pressure solve overlaps with the other's transport (measured at 128^2 x 1024 members
+    with k_sat_tb: forward run 1105 -> 1019 ms, bench value +8 .. +15 %; results bit-identical,
+    tests/test_sim_gpu.py::test_concurrent_lanes_are_bit_identical).  ``lanes = 0``: 2 where an on-chip transport kernel
+    runs and the ensemble has at least 256 members, else 1.  ``stats`` are summed over the lanes (phase times therefore
+    add up to more than the wall time).
     """
     use_torch = _is_torch(K)
     counts = [x.shape[0] for x, nd in ((K, 2), (S0, 2), (well_cell, 2), (well_rate, 3))
