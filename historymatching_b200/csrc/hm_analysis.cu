@@ -134,7 +134,8 @@ k_local_analysis(int64_t M, int p, double nm1, const double* __restrict__ A,
     double* c = sm;           // [p] sqrt(taper) of active obs
     double* rhs = sm + p;     // [p]
     int* idx = (int*)(sm + 2 * p);  // [p] active obs indices
-    double* L = sm + 2 * p + (p + 1) / 2;  // lower triangle, packed by rows: (a, b <= a) at a (a + 1) / 2 + b
+    double* colk = sm + 2 * p + (p + 1) / 2;  // [p] the current column of the factor, contiguous (conflict-free reads)
+    double* L = colk + p;  // lower triangle, packed by rows: (a, b <= a) at a (a + 1) / 2 + b
     __shared__ int s_n;
     __shared__ int s_fail;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -157,9 +158,13 @@ k_local_analysis(int64_t M, int p, double nm1, const double* __restrict__ A,
     __syncthreads();
     const int n = s_n;
     for (int a = tid; a < n; a += nt) rhs[a] = c[a] * B[(int64_t)idx[a] * ldB + i];
-    for (int e = tid; e < n * n; e += nt) {
-        const int a = e / n, b = e % n;
-        if (b <= a) L[tri(a, b)] = c[a] * c[b] * A[(int64_t)idx[a] * p + idx[b]] + (a == b ? nm1 : 0.0);
+    // rows of the triangle go to warps, the columns b <= a of a row to lanes: no integer division in the loops
+    const int lane = tid & 31, wrp = tid >> 5, nwarp = nt >> 5;
+    for (int a = wrp; a < n; a += nwarp) {
+        const double ca = c[a];
+        const double* Arow = A + (int64_t)idx[a] * p;
+        double* La = L + tri(a, 0);
+        for (int b = lane; b <= a; b += 32) La[b] = ca * c[b] * Arow[idx[b]] + (a == b ? nm1 : 0.0);
     }
     __syncthreads();
     // right-looking Cholesky
@@ -168,12 +173,16 @@ k_local_analysis(int64_t M, int p, double nm1, const double* __restrict__ A,
         if (tid == 0 && !(dkk > 0.0)) s_fail = 1;
         const double d = sqrt(dkk);
         __syncthreads();
-        for (int a = k + tid; a < n; a += nt) L[tri(a, k)] = (a == k) ? d : L[tri(a, k)] / d;
+        for (int a = k + tid; a < n; a += nt) {
+            const double v = (a == k) ? d : L[tri(a, k)] / d;
+            L[tri(a, k)] = v;
+            colk[a] = v;
+        }
         __syncthreads();
-        const int rem = n - k - 1;
-        for (int e = tid; e < rem * rem; e += nt) {
-            const int a = k + 1 + e / rem, b = k + 1 + e % rem;
-            if (b <= a) L[tri(a, b)] -= L[tri(a, k)] * L[tri(b, k)];
+        for (int a = k + 1 + wrp; a < n; a += nwarp) {
+            const double lak = colk[a];
+            double* La = L + tri(a, 0);
+            for (int b = k + 1 + lane; b <= a; b += 32) La[b] -= lak * colk[b];
         }
         __syncthreads();
     }
@@ -217,7 +226,7 @@ k_iles_step(int N, int64_t M, int p, double xStep, const double* __restrict__ S,
     // of a global-memory workspace - same algorithm, no size limit (the notebook's N = 200 runs this way).
     extern __shared__ double sm_dyn[];
     double* sm = gws ? gws + blockIdx.x * gws_stride : sm_dyn;
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wrp = tid >> 5, nwarp = nt >> 5;
     for (int64_t ip = blockIdx.x; ip < M; ip += gridDim.x) {
     __syncthreads();  // the workspace and the flags are reused by this CTA's next parameter
     double* A = sm;                 // N*N  : Wi -> Wi^-1 -> centred
@@ -289,19 +298,16 @@ k_iles_step(int N, int64_t M, int p, double xStep, const double* __restrict__ S,
         __syncthreads();
         for (int j = tid; j < N; j += nt) A[k * N + j] = (j == k) ? dinv : A[k * N + j] * dinv;
         __syncthreads();
-        for (int e = tid; e < N * N; e += nt) {
-            const int i = e / N, j = e % N;
-            if (i == k) continue;
-            const double f = A[i * N + k];
-            // column k of the other rows becomes -f * dinv, the rest is eliminated
-            if (j == k) Cc[i] = f;  // stash the multipliers: they are overwritten below
-        }
+        // column k of the other rows becomes -f * dinv, the rest is eliminated; the multipliers f are stashed first (they
+        // are overwritten).  Rows go to warps, columns to lanes: no integer division in the loops.
+        for (int i = tid; i < N; i += nt) Cc[i] = A[i * N + k];
         __syncthreads();
-        for (int e = tid; e < N * N; e += nt) {
-            const int i = e / N, j = e % N;
+        for (int i = wrp; i < N; i += nwarp) {
             if (i == k) continue;
             const double f = Cc[i];
-            A[i * N + j] = (j == k) ? -f * dinv : A[i * N + j] - f * A[k * N + j];
+            double* Ai = A + i * N;
+            const double* Ak = A + k * N;
+            for (int j = lane; j < N; j += 32) Ai[j] = (j == k) ? -f * dinv : Ai[j] - f * Ak[j];
         }
         __syncthreads();
     }
@@ -322,28 +328,30 @@ k_iles_step(int N, int64_t M, int p, double xStep, const double* __restrict__ S,
         colmean[j] = sacc / (double)N;
     }
     __syncthreads();
-    for (int e = tid; e < N * N; e += nt) A[e] -= colmean[e % N];
+    for (int i = wrp; i < N; i += nwarp)
+        for (int j = lane; j < N; j += 32) A[i * N + j] -= colmean[j];
     __syncthreads();
     // Y0 = A Si,  Si[k][a] = S[k][idx[a]] c[a]
-    for (int e = tid; e < N * n; e += nt) {
-        const int r = e / n, a = e % n;
-        double acc = 0.0;
-        for (int k = 0; k < N; ++k) acc = fma(A[r * N + k], S[(int64_t)k * p + idx[a]], acc);
-        Y0[r * n + a] = acc * c[a];
-    }
+    for (int r = wrp; r < N; r += nwarp)
+        for (int a = lane; a < n; a += 32) {
+            double acc = 0.0;
+            for (int k = 0; k < N; ++k) acc = fma(A[r * N + k], S[(int64_t)k * p + idx[a]], acc);
+            Y0[r * n + a] = acc * c[a];
+        }
     __syncthreads();
     // G = Di Y0^T + (N-1)(I - Wi) ;  C = Y0 Y0^T + (N-1) I
-    for (int e = tid; e < N * N; e += nt) {
-        const int r = e / N, l = e % N;
-        double g = 0.0, cc = 0.0;
-        for (int a = 0; a < n; ++a) {
-            const double y = Y0[l * n + a];
-            g = fma(D[(int64_t)r * p + idx[a]] * c[a], y, g);
-            cc = fma(Y0[r * n + a], y, cc);
+    for (int r = wrp; r < N; r += nwarp)
+        for (int l = lane; l < N; l += 32) {
+            double g = 0.0, cc = 0.0;
+            for (int a = 0; a < n; ++a) {
+                const double y = Y0[l * n + a];
+                g = fma(D[(int64_t)r * p + idx[a]] * c[a], y, g);
+                cc = fma(Y0[r * n + a], y, cc);
+            }
+            const int e = r * N + l;
+            G[e] = g + nm1 * ((r == l ? 1.0 : 0.0) - W[e]);
+            Cc[e] = cc + (r == l ? nm1 : 0.0);
         }
-        G[e] = g + nm1 * ((r == l ? 1.0 : 0.0) - W[e]);
-        Cc[e] = cc + (r == l ? nm1 : 0.0);
-    }
     __syncthreads();
     // Cholesky of C (lower, in place)
     for (int k = 0; k < N; ++k) {
@@ -353,10 +361,9 @@ k_iles_step(int N, int64_t M, int p, double xStep, const double* __restrict__ S,
         __syncthreads();
         for (int a = k + tid; a < N; a += nt) Cc[a * N + k] = (a == k) ? d : Cc[a * N + k] / d;
         __syncthreads();
-        const int rem = N - k - 1;
-        for (int e = tid; e < rem * rem; e += nt) {
-            const int a = k + 1 + e / rem, b = k + 1 + e % rem;
-            if (b <= a) Cc[a * N + b] -= Cc[a * N + k] * Cc[b * N + k];
+        for (int a = k + 1 + wrp; a < N; a += nwarp) {
+            const double cak = Cc[a * N + k];
+            for (int b = k + 1 + lane; b <= a; b += 32) Cc[a * N + b] -= cak * Cc[b * N + k];
         }
         __syncthreads();
     }
@@ -527,7 +534,7 @@ extern "C" int hm_les_update(hm_ctx* ctx, int64_t N, int64_t M, int64_t p, doubl
     HM_REQUIRE(ctx && E && Eo && obs && perturbs && decorr && taper, "null pointer");
     HM_REQUIRE(N > 1 && M > 0 && p > 0 && ldE >= M, "shape");
     HM_CUDA(cudaSetDevice(ctx->device));
-    size_t smem = ((size_t)2 * p + (p + 1) / 2 + (size_t)p * (p + 1) / 2) * sizeof(double);  // packed lower triangle: two CTAs per SM at p = 160
+    size_t smem = ((size_t)3 * p + (p + 1) / 2 + (size_t)p * (p + 1) / 2) * sizeof(double);  // packed lower triangle: two CTAs per SM at p = 160
     double *S, *D, *A, *B;
     int* fail;
     HM_CHECK(whiten(ctx, N, p, Eo, obs, perturbs, decorr, &S, &D));

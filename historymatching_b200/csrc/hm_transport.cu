@@ -598,6 +598,7 @@ int transport_tb(hm_ctx* ctx, const hm_sim_desc& d, const Fluid& fl, const Wells
                 best_active * csize, ctx->sm_count);
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
+    if (getenv("HM_TB_MAX_CLUSTERS")) best_active = std::max(1, std::min(best_active, atoi(getenv("HM_TB_MAX_CLUSTERS"))));  // development
     a.nWork = nm * a.nStrips;
     tb_launch_cfg(&cfg, attr, W, csize, (unsigned)(std::min(a.nWork, best_active) * csize), st);
     const int kround = a.nStrips == 1 ? max_nts : a.halo;
