@@ -430,8 +430,23 @@ int check_info(hm_ctx* ctx, int* d_info, const char* what) {
     return HM_OK;
 }
 
-// Cholesky factor of the SPD n x n matrix A (row-major == column-major by symmetry), in place.
-int chol_factor(hm_ctx* ctx, int n, double* A) {
+// check the first `count` info words of "an.info" with ONE stream synchronisation (deferred checks of a call sequence)
+int check_infos(hm_ctx* ctx, int count, const char* what) {
+    int* info;
+    HM_CHECK(ctx->ws.get("an.info", (size_t)4, &info));
+    HM_CUDA(cudaMemcpyAsync(ctx->h_pinned, info, count * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    HM_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < count; ++i)
+        if (ctx->h_pinned[i] != 0) {
+            hm::set_error("%s failed: info[%d] = %d", what, i, ctx->h_pinned[i]);
+            return HM_ERR_NUMERIC;
+        }
+    return HM_OK;
+}
+
+// Cholesky factor of the SPD n x n matrix A (row-major == column-major by symmetry), in place.  slot >= 0: the status
+// goes to word `slot` of "an.info" and is NOT checked here (no host synchronisation): the caller ends with check_infos.
+int chol_factor(hm_ctx* ctx, int n, double* A, int slot = -1) {
     HM_CHECK(ensure_solver(ctx));
     int lwork = 0;
     HM_CUSOLVER(cusolverDnDpotrf_bufferSize(ctx->solver, CUBLAS_FILL_MODE_LOWER, n, A, n, &lwork));
@@ -439,16 +454,16 @@ int chol_factor(hm_ctx* ctx, int n, double* A) {
     int* info;
     HM_CHECK(ctx->ws.get("an.potrf_work", (size_t)std::max(lwork, 1), &work));
     HM_CHECK(ctx->ws.get("an.info", (size_t)4, &info));
-    HM_CUSOLVER(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, n, A, n, work, lwork, info));
-    return check_info(ctx, info, "Cholesky factorisation (potrf)");
+    HM_CUSOLVER(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, n, A, n, work, lwork, info + std::max(slot, 0)));
+    return slot >= 0 ? HM_OK : check_info(ctx, info, "Cholesky factorisation (potrf)");
 }
 // In place: Brow (nrhs x n, row-major) <- Brow A^-1, using the factor from chol_factor.
 // (column-major view of Brow is n x nrhs = Brow^T, and A^-1 Brow^T = (Brow A^-1)^T.)
-int chol_solve_right(hm_ctx* ctx, int n, const double* Afac, int nrhs, double* Brow) {
+int chol_solve_right(hm_ctx* ctx, int n, const double* Afac, int nrhs, double* Brow, int slot = -1) {
     int* info;
     HM_CHECK(ctx->ws.get("an.info", (size_t)4, &info));
-    HM_CUSOLVER(cusolverDnDpotrs(ctx->solver, CUBLAS_FILL_MODE_LOWER, n, nrhs, Afac, n, Brow, n, info));
-    return check_info(ctx, info, "Cholesky solve (potrs)");
+    HM_CUSOLVER(cusolverDnDpotrs(ctx->solver, CUBLAS_FILL_MODE_LOWER, n, nrhs, Afac, n, Brow, n, info + std::max(slot, 0)));
+    return slot >= 0 ? HM_OK : check_info(ctx, info, "Cholesky solve (potrs)");
 }
 
 }  // namespace
@@ -496,13 +511,15 @@ extern "C" int hm_es_update(hm_ctx* ctx, int64_t N, int64_t M, int64_t p, double
     HM_CHECK(hm::dgemm(ctx, true, false, p, p, N, 1.0, S, p, S, p, 0.0, C, p));
     k_add_diag<<<(unsigned)((p + 127) / 128), 128, 0, ctx->stream>>>(p, C, p, (double)(N - 1));
     ctx->launches += 1;
-    HM_CHECK(chol_factor(ctx, (int)p, C));
+    // one host synchronisation for the whole update (the factorisation status is checked at the end): the update is a
+    // dozen short launches, and every host round trip between them is exposed to the host's scheduling noise
+    HM_CHECK(chol_factor(ctx, (int)p, C, 0));
     // D <- D C^-1
-    HM_CHECK(chol_solve_right(ctx, (int)p, C, (int)N, D));
+    HM_CHECK(chol_solve_right(ctx, (int)p, C, (int)N, D, 1));
     // G = S^T E ; E += (D C^-1) G
     HM_CHECK(hm::dgemm(ctx, true, false, p, M, N, 1.0, S, p, E, ldE, 0.0, G, M));
     HM_CHECK(hm::dgemm(ctx, false, false, N, M, p, 1.0, D, p, G, M, 1.0, E, ldE));
-    return HM_OK;
+    return check_infos(ctx, 2, "ES update: Cholesky factorisation / solve of S^T S + (N-1) I");
 }
 
 extern "C" int hm_es_update_host(hm_ctx* ctx, int64_t N, int64_t M, int64_t p, double* E,
