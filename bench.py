@@ -463,8 +463,13 @@ def measure(args, wl, rank, world, local_rank, dev, steps, warmup, full):
         if world > 1:
             dist.barrier()  # the ranks' forward runs end at slightly different times: keep that wait out of update_ms
         t0.record()
+        h0 = time.perf_counter()
         post = hd.es_update_sharded(E, Eo, N, noisy, pert, dec)
         t1.record()
+        if os.environ.get("HM_BENCH_LOG"):
+            h1 = time.perf_counter()
+            torch.cuda.synchronize()
+            log("update: host call %.2f ms, with sync %.2f ms, events %.2f ms" % (1e3 * (h1 - h0), 1e3 * (time.perf_counter() - h0), t0.elapsed_time(t1)))
         last["upd"] = (t0, t1)
         return post, Eo
 
