@@ -57,7 +57,6 @@ struct TbArgs {
     double* Sout;
     const double* Vxl;
     const double* Vyl;
-    int probe;  // development: HM_TB_PROBE bits (1 = no halo traffic, 2 = no wells, 4 = no CTA barrier); results invalid
 };
 
 // upwind value of a face with signed coefficient w (flow from the low to the high cell when w > 0); the sign test
@@ -112,8 +111,7 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_sat_tb(TbArgs a, Fluid fl, We
     // halo exchange: this thread's one row neighbour (up or down) and one column neighbour (left or right)
     const uint32_t bar0 = smem_u32(&bars[0]), bar1 = smem_u32(&bars[1]), ldbar = smem_u32(&bars[2]), ctabar = smem_u32(&bars[3]);
     int cpar = 0;
-    const bool hx_ = !(a.probe & 1);
-    const bool hasUp = hx_ && cxi > 0, hasDn = hx_ && cxi < a.cx - 1, hasLf = hx_ && cyi > 0, hasRt = hx_ && cyi < a.cy - 1;
+    const bool hasUp = cxi > 0, hasDn = cxi < a.cx - 1, hasLf = cyi > 0, hasRt = cyi < a.cy - 1;
     const int haloBytes = 8 * (W * ((int)hasUp + (int)hasDn) + R * ((int)hasLf + (int)hasRt));
     if (tid == 0) {
         mbar_init(bar0, 1);
@@ -232,7 +230,9 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_sat_tb(TbArgs a, Fluid fl, We
         // Split CTA barrier (an mbarrier counting all threads): arrive as soon as this thread's fw values are published, wait
         // only where the neighbours' values are needed - the halo sends, the faces inside the patch and the well terms of
         // a warp overlap with the other warps' publishing (measured at 128^2: 18.2 -> 16.2 ms per launch against bar.sync)
-        if (!(a.probe & 4)) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ctabar) : "memory");
+        // (whole-row tiles: the barrier operations sit behind a branch on a run-time constant - a scheduling fence for ptxas,
+        // which otherwise sinks the arrive below the sends and the interior faces: measured at 512^2, 488 vs 459 ms per step)
+        if (NQ > 2 || a.kmax > 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ctabar) : "memory");
         // edge rows / columns into the neighbours' halo slots.  (STAS cannot be predicated: one branch per direction,
         // the row direction is warp-uniform, the column direction is taken by one lane per warp.)
         if (NQ > 2 && sX) {
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_sat_tb(TbArgs a, Fluid fl, We
                 }
             }
         }
-        if (!(a.probe & 4)) {
+        if (NQ > 2 || a.kmax > 0) {
             mbar_wait(ctabar, cpar);
             cpar ^= 1;
         }
@@ -343,15 +343,6 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_sat_tb(TbArgs a, Fluid fl, We
     };
     double* const fwa = fb0 + tb;
     double* const fwb = fb1 + tb;
-    __shared__ long long tstamp[8][6];
-    const bool trace = (a.probe & 32) && blockIdx.x < csize && a.it0 == a.kmax && tid == 0;
-    auto stamp = [&](int item, int k) {
-        if (trace && item < 8) {
-            long long t;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            tstamp[item][k] = t;
-        }
-    };
     int gsub = 0;  // sub-steps executed by this cluster so far: buffer = gsub & 1, mbarrier phase = (gsub >> 1) & 1
 
     for (int item = 0; work < nWork; work += nClusters, ++item) {
@@ -363,7 +354,6 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_sat_tb(TbArgs a, Fluid fl, We
         const int slot = item & 1;
 
         // staged tile -> registers.  Rows beyond the grid hold S = 0 and zero coefficients: inert.
-        stamp(item, 0);
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();  // this item's wells and sub-step count (cp.async of other threads) are visible
         const int n = ntss[slot];
@@ -390,7 +380,6 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_sat_tb(TbArgs a, Fluid fl, We
             wl_pos[e] = fmax(qs, 0.0);
         }
         mbar_wait(ldbar, item & 1);
-        stamp(item, 1);
 #pragma unroll
         for (int r = 0; r < 5; ++r) {
             wx[r][0] = wx[r][1] = 0.0;
@@ -424,8 +413,6 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_sat_tb(TbArgs a, Fluid fl, We
         wcode = -1;
         for (int e = nwl - 1; e >= 0; --e)
             if (wl_tid[e] == tid) wcode = e | (wl_slot[e] << 8) | (wcode >= 0 ? 1 << 16 : 0);
-        if (a.probe & 2) wcode = -1;
-        stamp(item, 2);
 
         int sub = 0;
         if ((gsub & 1) && nr > 0) {  // an odd number of sub-steps so far: the next one uses the second buffer
@@ -441,7 +428,6 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_sat_tb(TbArgs a, Fluid fl, We
             substep(fwa, bar0, xa0, xb0, ya0, yb0, (gsub >> 1) & 1);
             ++gsub;
         }
-        stamp(item, 3);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int gr = row0 + r;
@@ -449,13 +435,6 @@ __global__ void __launch_bounds__(kTbThreads, 1) k_sat_tb(TbArgs a, Fluid fl, We
                 *reinterpret_cast<double2*>(a.Sout + (int64_t)m * a.M + (int64_t)gr * a.Ny + col0 + 2 * c) =
                     make_double2(S[r][0], S[r][1]);
         }
-        stamp(item, 4);
-    }
-    if (trace) {
-        for (int i = 0; i < 6; ++i)
-            printf("[tb trace] cta %2d item %d: wait-load %6lld  setup %6lld  loop %6lld  store %6lld | item start +%lld ns\n", rank, i,
-                   tstamp[i][1] - tstamp[i][0], tstamp[i][2] - tstamp[i][1], tstamp[i][3] - tstamp[i][2],
-                   tstamp[i][4] - tstamp[i][3], tstamp[i][0] - tstamp[0][0]);
     }
 }
 
@@ -586,7 +565,6 @@ int transport_tb(hm_ctx* ctx, const hm_sim_desc& d, const Fluid& fl, const Wells
     a.nts = nts;
     a.Vxl = Vxl;
     a.Vyl = Vyl;
-    a.probe = getenv("HM_TB_PROBE") ? atoi(getenv("HM_TB_PROBE")) : 0;
     const int csize = a.cx * a.cy;
     ctx->sim_stats.sat_resident_ctas = (int64_t)best_active * csize;
     ctx->sim_stats.sat_tb_cluster = csize;
