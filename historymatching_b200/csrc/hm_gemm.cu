@@ -65,15 +65,18 @@ __device__ __forceinline__ void store_tile(const Operand& op, double* sm,
             if (e < ROWS * BK) sm[(e / BK) * LDS + (e % BK)] = reg[j];
         }
     } else {
+        // operand whose rows are contiguous in memory (k strided): kept k-major in shared memory, sm[k][row] with a pitch of
+        // ROWS + 4 doubles - consecutive lanes store consecutive rows (the [row][k] layout gave 4-way bank conflicts here)
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
             const int e = threadIdx.x + j * NT;
-            if (e < ROWS * BK) sm[(e % ROWS) * LDS + (e / ROWS)] = reg[j];
+            if (e < ROWS * BK) sm[(e / ROWS) * (ROWS + 4) + (e % ROWS)] = reg[j];
         }
     }
 }
 
-template <int WM, int WN>
+// AKM / BKM: the operand is k-major in shared memory (its rows are contiguous in global memory, see store_tile)
+template <int WM, int WN, bool AKM, bool BKM>
 __global__ void __launch_bounds__(WM * WN * 32)
 k_dgemm(Operand A, Operand B, int64_t K, double alpha, double beta, double* __restrict__ C,
         int64_t ldc) {
@@ -105,15 +108,17 @@ k_dgemm(Operand A, Operand B, int64_t K, double alpha, double beta, double* __re
             load_tile<BM, NT>(A, row0, (kt + 1) * BK, K, ra);
             load_tile<BN, NT>(B, col0, (kt + 1) * BK, K, rb);
         }
-        const double* as = As + cur * BM * LDS + (wm * 32 + g) * LDS + q;
-        const double* bs = Bs + cur * BN * LDS + (wn * 32 + g) * LDS + q;
+        // fragment element (row 8 i + g, k = ks + q): [row][k] layout (pitch LDS) or [k][row] layout (pitch ROWS + 4); both
+        // are conflict-free 64-bit loads (per half-warp: 4 values of g x 4 of q on 16 distinct banks)
+        const double* as = As + cur * BM * LDS + (AKM ? q * (BM + 4) + wm * 32 + g : (wm * 32 + g) * LDS + q);
+        const double* bs = Bs + cur * BN * LDS + (BKM ? q * (BN + 4) + wn * 32 + g : (wn * 32 + g) * LDS + q);
 #pragma unroll
         for (int ks = 0; ks < BK; ks += 4) {
             double a[4], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = as[i * 8 * LDS + ks];
+            for (int i = 0; i < 4; ++i) a[i] = AKM ? as[ks * (BM + 4) + i * 8] : as[i * 8 * LDS + ks];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = bs[j * 8 * LDS + ks];
+            for (int j = 0; j < 4; ++j) b[j] = BKM ? bs[ks * (BN + 4) + j * 8] : bs[j * 8 * LDS + ks];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -151,18 +156,27 @@ k_dgemm(Operand A, Operand B, int64_t K, double alpha, double beta, double* __re
     }
 }
 
-template <int WM, int WN>
-int launch(hm_ctx* ctx, const Operand& A, const Operand& B, int64_t K, double alpha, double beta,
-           double* C, int64_t ldc) {
+template <int WM, int WN, bool AKM, bool BKM>
+int launch2(hm_ctx* ctx, const Operand& A, const Operand& B, int64_t K, double alpha, double beta, double* C, int64_t ldc) {
     constexpr int BM = 32 * WM, BN = 32 * WN;
     const size_t smem = (size_t)2 * (BM + BN) * LDS * sizeof(double);
     // per launch: the attribute belongs to the current device's context (a process may drive several GPUs)
-    HM_CUDA(cudaFuncSetAttribute(k_dgemm<WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HM_CUDA(cudaFuncSetAttribute(k_dgemm<WM, WN, AKM, BKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((B.rows + BN - 1) / BN), (unsigned)((A.rows + BM - 1) / BM));
-    k_dgemm<WM, WN><<<grid, WM * WN * 32, smem, ctx->stream>>>(A, B, K, alpha, beta, C, ldc);
+    k_dgemm<WM, WN, AKM, BKM><<<grid, WM * WN * 32, smem, ctx->stream>>>(A, B, K, alpha, beta, C, ldc);
     HM_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return HM_OK;
+}
+
+template <int WM, int WN>
+int launch(hm_ctx* ctx, const Operand& A, const Operand& B, int64_t K, double alpha, double beta,
+           double* C, int64_t ldc) {
+    const bool akm = A.s_k != 1, bkm = B.s_k != 1;  // the shared-memory layout follows the operand's unit-stride direction
+    if (akm) return bkm ? launch2<WM, WN, true, true>(ctx, A, B, K, alpha, beta, C, ldc)
+                        : launch2<WM, WN, true, false>(ctx, A, B, K, alpha, beta, C, ldc);
+    return bkm ? launch2<WM, WN, false, true>(ctx, A, B, K, alpha, beta, C, ldc)
+               : launch2<WM, WN, false, false>(ctx, A, B, K, alpha, beta, C, ldc);
 }
 
 }  // namespace
