@@ -7,20 +7,45 @@
 //
 // C[m,n] = alpha * op(A)[m,k] * op(B)[k,n] + beta * C, everything row-major.
 // CTA tile (32*WM) x (32*WN) x 16, one warp per 32x32 sub-tile (4x4 DMMA
-// tiles, 64 accumulator registers), operands staged in shared memory as
-// As[m][k], Bs[n][k] with a row pitch of 20 doubles (conflict-free 64-bit
-// fragment loads), register-prefetched double buffering.
+// tiles, 64 accumulator registers).  Operands are staged in shared memory by
+// cp.async (LDGSTS, zero-filled outside the matrices) through a 3-stage ring:
+// a "full" mbarrier per stage completes when every thread's copies of that
+// k-block have landed (cp.async.mbarrier.arrive), an "empty" mbarrier when all
+// warps have consumed it.  There is no CTA-wide barrier in the main loop, so a
+// warp can run up to one k-block ahead of the slowest one and the FP64 pipe is
+// not drained at every block (the register-prefetch version lost 10 % of its
+// stall samples at its __syncthreads and ran at 0.75 of cuBLAS).
+// Layout per stage: As[m][k], Bs[n][k] with a row pitch of 20 doubles, or
+// k-major [k][row] with a pitch of rows + 4 for an operand whose rows are
+// contiguous in memory - conflict-free 64-bit fragment loads in both.
 #include "hm_common.cuh"
+#include "hm_ptx.cuh"
 
 namespace {
 
+using hmsim::mbar_init;
+using hmsim::mbar_wait;
+using hmsim::smem_u32;
+
 constexpr int BK = 16;
 constexpr int LDS = BK + 4;
+constexpr int STAGES = 3;
 
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
+}
+// 8-byte asynchronous copy; src_bytes = 0 writes zeros and does not touch the source
+__device__ __forceinline__ void cp_async_8z(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// arrive on `bar` once all cp.async issued so far by this thread have completed (the barrier's count includes it)
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 // Element (row i, reduction index kk) of a "rows x k" operand lives at base[i*s_row + kk*s_k].
@@ -30,64 +55,50 @@ struct Operand {
     int64_t rows;
 };
 
-template <int ROWS, int NT>
-__device__ __forceinline__ void load_tile(const Operand& op, int64_t row0, int64_t k0, int64_t K,
-                                          double (&reg)[(ROWS * BK + NT - 1) / NT]) {
+// Issue the copies of one ROWS x BK operand block into a stage.  KM: the operand's rows are contiguous in memory
+// (s_row == 1), consecutive threads take consecutive rows and the stage is k-major; otherwise s_k == 1 and
+// consecutive threads run along k.
+template <int ROWS, int NT, bool KM>
+__device__ __forceinline__ void issue_tile(const Operand& op, int64_t row0, int64_t k0, int64_t K, double* sm) {
     constexpr int PER = (ROWS * BK + NT - 1) / NT;
-    // thread -> element mapping runs fastest along the unit-stride direction of the operand
-    if (op.s_k == 1) {
 #pragma unroll
-        for (int j = 0; j < PER; ++j) {
-            const int e = threadIdx.x + j * NT;
-            const int kk = e % BK, r = e / BK;
+    for (int j = 0; j < PER; ++j) {
+        const int e = threadIdx.x + j * NT;
+        if (e < ROWS * BK) {
+            const int r = KM ? e % ROWS : e / BK, kk = KM ? e / ROWS : e % BK;
             const int64_t gr = row0 + r, gk = k0 + kk;
-            reg[j] = (e < ROWS * BK && gr < op.rows && gk < K) ? op.base[gr * op.s_row + gk] : 0.0;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < PER; ++j) {
-            const int e = threadIdx.x + j * NT;
-            const int r = e % ROWS, kk = e / ROWS;
-            const int64_t gr = row0 + r, gk = k0 + kk;
-            reg[j] = (e < ROWS * BK && gr < op.rows && gk < K) ? op.base[gr * op.s_row + gk * op.s_k] : 0.0;
+            const bool ok = gr < op.rows && gk < K;
+            const double* src = ok ? op.base + gr * op.s_row + gk * op.s_k : op.base;
+            cp_async_8z(smem_u32(sm + (KM ? kk * (ROWS + 4) + r : r * LDS + kk)), src, ok ? 8 : 0);
         }
     }
 }
 
-template <int ROWS, int NT>
-__device__ __forceinline__ void store_tile(const Operand& op, double* sm,
-                                           const double (&reg)[(ROWS * BK + NT - 1) / NT]) {
-    constexpr int PER = (ROWS * BK + NT - 1) / NT;
-    if (op.s_k == 1) {
-#pragma unroll
-        for (int j = 0; j < PER; ++j) {
-            const int e = threadIdx.x + j * NT;
-            if (e < ROWS * BK) sm[(e / BK) * LDS + (e % BK)] = reg[j];
-        }
-    } else {
-        // operand whose rows are contiguous in memory (k strided): kept k-major in shared memory, sm[k][row] with a pitch of
-        // ROWS + 4 doubles - consecutive lanes store consecutive rows (the [row][k] layout gave 4-way bank conflicts here)
-#pragma unroll
-        for (int j = 0; j < PER; ++j) {
-            const int e = threadIdx.x + j * NT;
-            if (e < ROWS * BK) sm[(e / ROWS) * (ROWS + 4) + (e % ROWS)] = reg[j];
-        }
-    }
-}
-
-// AKM / BKM: the operand is k-major in shared memory (its rows are contiguous in global memory, see store_tile)
+// AKM / BKM: the operand is k-major in shared memory (its rows are contiguous in global memory, see issue_tile)
 template <int WM, int WN, bool AKM, bool BKM>
 __global__ void __launch_bounds__(WM * WN * 32)
 k_dgemm(Operand A, Operand B, int64_t K, double alpha, double beta, double* __restrict__ C,
         int64_t ldc) {
-    constexpr int BM = 32 * WM, BN = 32 * WN, NT = WM * WN * 32;
-    extern __shared__ double smem[];
-    double* As = smem;                  // [2][BM][LDS]
-    double* Bs = smem + 2 * BM * LDS;   // [2][BN][LDS]
+    constexpr int BM = 32 * WM, BN = 32 * WN, NT = WM * WN * 32, NW = WM * WN;
+    constexpr int STAGE = (BM + BN) * LDS;  // doubles per stage: A block, then B block
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bars[2 * STAGES];  // full[s], empty[s]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wm = warp / WN, wn = warp % WN;
     const int64_t row0 = (int64_t)blockIdx.y * BM, col0 = (int64_t)blockIdx.x * BN;
     const int g = lane >> 2, q = lane & 3;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (STAGES + s); };
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full(s), NT);
+            mbar_init(empty(s), NW);
+        }
+    }
+    __syncthreads();
 
     double acc[4][4][2];
 #pragma unroll
@@ -95,23 +106,25 @@ k_dgemm(Operand A, Operand B, int64_t K, double alpha, double beta, double* __re
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    double ra[(BM * BK + NT - 1) / NT], rb[(BN * BK + NT - 1) / NT];
     const int64_t nk = (K + BK - 1) / BK;
-    load_tile<BM, NT>(A, row0, 0, K, ra);
-    load_tile<BN, NT>(B, col0, 0, K, rb);
-    store_tile<BM, NT>(A, As, ra);
-    store_tile<BN, NT>(B, Bs, rb);
-    __syncthreads();
+    auto issue = [&](int64_t kb, int s) {  // k-block kb -> stage s
+        double* as = smem + s * STAGE;
+        issue_tile<BM, NT, AKM>(A, row0, kb * BK, K, as);
+        issue_tile<BN, NT, BKM>(B, col0, kb * BK, K, as + BM * LDS);
+        cp_async_arrive(full(s));
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s)
+        if (s < nk) issue(s, s);
+
+    int s = 0, ph = 0;            // stage / parity of k-block kt
+    int sp = STAGES - 1, php = 1; // stage / parity of k-block kt - 1 (refilled with block kt + STAGES - 1)
     for (int64_t kt = 0; kt < nk; ++kt) {
-        const int cur = kt & 1;
-        if (kt + 1 < nk) {
-            load_tile<BM, NT>(A, row0, (kt + 1) * BK, K, ra);
-            load_tile<BN, NT>(B, col0, (kt + 1) * BK, K, rb);
-        }
+        mbar_wait(full(s), ph);
         // fragment element (row 8 i + g, k = ks + q): [row][k] layout (pitch LDS) or [k][row] layout (pitch ROWS + 4); both
         // are conflict-free 64-bit loads (per half-warp: 4 values of g x 4 of q on 16 distinct banks)
-        const double* as = As + cur * BM * LDS + (AKM ? q * (BM + 4) + wm * 32 + g : (wm * 32 + g) * LDS + q);
-        const double* bs = Bs + cur * BN * LDS + (BKM ? q * (BN + 4) + wn * 32 + g : (wn * 32 + g) * LDS + q);
+        const double* as = smem + s * STAGE + (AKM ? q * (BM + 4) + wm * 32 + g : (wm * 32 + g) * LDS + q);
+        const double* bs = smem + s * STAGE + BM * LDS + (BKM ? q * (BN + 4) + wn * 32 + g : (wn * 32 + g) * LDS + q);
 #pragma unroll
         for (int ks = 0; ks < BK; ks += 4) {
             double a[4], b[4];
@@ -124,11 +137,18 @@ k_dgemm(Operand A, Operand B, int64_t K, double alpha, double beta, double* __re
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
-        if (kt + 1 < nk) {
-            store_tile<BM, NT>(A, As + (cur ^ 1) * BM * LDS, ra);
-            store_tile<BN, NT>(B, Bs + (cur ^ 1) * BN * LDS, rb);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty(s));  // this warp is done with block kt
+        if (kt + STAGES - 1 < nk) {
+            if (kt > 0) mbar_wait(empty(sp), php);  // every warp is done with block kt - 1: its stage can be refilled
+            issue(kt + STAGES - 1, sp);
         }
-        __syncthreads();
+        sp = s;
+        php = ph;
+        if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+        }
     }
     // epilogue: lane holds C[g][2q], C[g][2q+1] of every 8x8 tile
 #pragma unroll
@@ -159,7 +179,7 @@ k_dgemm(Operand A, Operand B, int64_t K, double alpha, double beta, double* __re
 template <int WM, int WN, bool AKM, bool BKM>
 int launch2(hm_ctx* ctx, const Operand& A, const Operand& B, int64_t K, double alpha, double beta, double* C, int64_t ldc) {
     constexpr int BM = 32 * WM, BN = 32 * WN;
-    const size_t smem = (size_t)2 * (BM + BN) * LDS * sizeof(double);
+    const size_t smem = (size_t)STAGES * (BM + BN) * LDS * sizeof(double);
     // per launch: the attribute belongs to the current device's context (a process may drive several GPUs)
     HM_CUDA(cudaFuncSetAttribute(k_dgemm<WM, WN, AKM, BKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((B.rows + BN - 1) / BN), (unsigned)((A.rows + BM - 1) / BM));
