@@ -14,7 +14,9 @@
 // warps have consumed it.  There is no CTA-wide barrier in the main loop, so a
 // warp can run up to one k-block ahead of the slowest one and the FP64 pipe is
 // not drained at every block (the register-prefetch version lost 10 % of its
-// stall samples at its __syncthreads and ran at 0.75 of cuBLAS).
+// stall samples at its __syncthreads and ran at 0.75 of cuBLAS; this one
+// runs at 0.92 - 0.93).  Copies are 16 bytes wide where the operand's alignment
+// allows, 8 bytes otherwise.
 // Layout per stage: As[m][k], Bs[n][k] with a row pitch of 20 doubles, or
 // k-major [k][row] with a pitch of rows + 4 for an operand whose rows are
 // contiguous in memory - conflict-free 64-bit fragment loads in both.
@@ -27,6 +29,9 @@ using hmsim::mbar_init;
 using hmsim::mbar_wait;
 using hmsim::smem_u32;
 
+// Measured on B200, W (1024 x 1024) @ X0 (1024 x 16384), TFLOP/s (cuBLAS 34.9): BK 16 x 3 stages 31.9; 4 stages 30.4;
+// BK 8 x 4 stages 29.9; BK 32 x 2 stages 26.7; 8-byte copies only 30.9; copies requested before instead of after the
+// block's multiplication 31.5 (profiles/dgemm_r2_shapes.txt).
 constexpr int BK = 16;
 constexpr int LDS = BK + 4;
 constexpr int STAGES = 3;
@@ -39,6 +44,10 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
 // 8-byte asynchronous copy; src_bytes = 0 writes zeros and does not touch the source
 __device__ __forceinline__ void cp_async_8z(uint32_t dst, const void* src, int src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// 16-byte copy past L1; src_bytes in {0, 8, 16}, the rest of the 16 bytes is zero-filled
+__device__ __forceinline__ void cp_async_16z(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 // arrive on `bar` once all cp.async issued so far by this thread have completed (the barrier's count includes it)
 __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
@@ -53,6 +62,7 @@ struct Operand {
     const double* base;
     int64_t s_row, s_k;
     int64_t rows;
+    int vec;  // 16-byte copies are possible: base 16-byte aligned, the non-unit stride even
 };
 
 // Issue the copies of one ROWS x BK operand block into a stage.  KM: the operand's rows are contiguous in memory
@@ -60,6 +70,22 @@ struct Operand {
 // consecutive threads run along k.
 template <int ROWS, int NT, bool KM>
 __device__ __forceinline__ void issue_tile(const Operand& op, int64_t row0, int64_t k0, int64_t K, double* sm) {
+    if (op.vec) {  // 16-byte copies of two elements adjacent along the unit-stride direction (alignment checked by the host)
+        constexpr int PER = (ROWS * BK / 2 + NT - 1) / NT;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int e = threadIdx.x + j * NT;
+            if (e < ROWS * BK / 2) {
+                const int r = KM ? 2 * (e % (ROWS / 2)) : e / (BK / 2), kk = KM ? e / (ROWS / 2) : 2 * (e % (BK / 2));
+                const int64_t gr = row0 + r, gk = k0 + kk;
+                const bool ok = gr < op.rows && gk < K;
+                const bool ok2 = KM ? gr + 1 < op.rows : gk + 1 < K;
+                const double* src = ok ? op.base + gr * op.s_row + gk * op.s_k : op.base;
+                cp_async_16z(smem_u32(sm + (KM ? kk * (ROWS + 4) + r : r * LDS + kk)), src, ok ? (ok2 ? 16 : 8) : 0);
+            }
+        }
+        return;
+    }
     constexpr int PER = (ROWS * BK + NT - 1) / NT;
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
@@ -113,13 +139,22 @@ k_dgemm(Operand A, Operand B, int64_t K, double alpha, double beta, double* __re
         issue_tile<BN, NT, BKM>(B, col0, kb * BK, K, as + BM * LDS);
         cp_async_arrive(full(s));
     };
+    // Block kt + PF is requested after block kt has been multiplied; it goes into the stage block kt - 1 used.
+    constexpr int PF = STAGES - 1;
+    const int nkb = (int)nk;
+    auto refill = [&](int kt) {
+        const int nb = kt + PF, lb = nb - STAGES;
+        if (nb < nkb) {
+            if (lb >= 0) mbar_wait(empty(lb % STAGES), (lb / STAGES) & 1);  // every warp is done with the stage's last block
+            issue(nb, nb % STAGES);
+        }
+    };
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s)
-        if (s < nk) issue(s, s);
+    for (int b = 0; b < PF; ++b)
+        if (b < nkb) issue(b, b);
 
-    int s = 0, ph = 0;            // stage / parity of k-block kt
-    int sp = STAGES - 1, php = 1; // stage / parity of k-block kt - 1 (refilled with block kt + STAGES - 1)
-    for (int64_t kt = 0; kt < nk; ++kt) {
+    int s = 0, ph = 0;  // stage / parity of k-block kt
+    for (int kt = 0; kt < nkb; ++kt) {
         mbar_wait(full(s), ph);
         // fragment element (row 8 i + g, k = ks + q): [row][k] layout (pitch LDS) or [k][row] layout (pitch ROWS + 4); both
         // are conflict-free 64-bit loads (per half-warp: 4 values of g x 4 of q on 16 distinct banks)
@@ -139,12 +174,7 @@ k_dgemm(Operand A, Operand B, int64_t K, double alpha, double beta, double* __re
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty(s));  // this warp is done with block kt
-        if (kt + STAGES - 1 < nk) {
-            if (kt > 0) mbar_wait(empty(sp), php);  // every warp is done with block kt - 1: its stage can be refilled
-            issue(kt + STAGES - 1, sp);
-        }
-        sp = s;
-        php = ph;
+        refill(kt);
         if (++s == STAGES) {
             s = 0;
             ph ^= 1;
@@ -208,8 +238,9 @@ int dgemm(hm_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_t k, double
           const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C,
           int64_t ldc) {
     if (m <= 0 || n <= 0) return HM_OK;
-    Operand a{A, tA ? 1 : lda, tA ? lda : 1, m};
-    Operand b{B, tB ? ldb : 1, tB ? 1 : ldb, n};
+    auto vec_ok = [](const double* p, int64_t ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % 2 == 0; };
+    Operand a{A, tA ? 1 : lda, tA ? lda : 1, m, vec_ok(A, lda)};
+    Operand b{B, tB ? ldb : 1, tB ? 1 : ldb, n, vec_ok(B, ldb)};
     auto padded = [&](int64_t bm, int64_t bn) {
         return ((m + bm - 1) / bm) * bm * (((n + bn - 1) / bn) * bn);
     };

@@ -137,6 +137,38 @@ def test_dgemm_dmma(m, n, k, tA, tB):
     np.testing.assert_allclose(dC.cpu().numpy(), ref, rtol=1e-12, atol=1e-12)
 
 
+@pytest.mark.parametrize("m,n,k,tA,tB,off", [(131, 77, 45, False, False, 0), (131, 77, 45, True, True, 0),
+                                             (33, 129, 19, True, False, 0), (70, 35, 35, False, True, 0),
+                                             (64, 64, 32, False, False, 1), (1, 3, 1, True, True, 0),
+                                             (40, 50, 0, False, False, 0)])
+def test_dgemm_submatrix_views(m, n, k, tA, tB, off):
+    """Operands that are windows of larger row-major arrays: even leading dimensions with odd extents (the last
+    16-byte copy of a row / column is half outside the matrix and must be zero-filled), a base that is only 8-byte
+    aligned (`off` = 1: the 8-byte copy path), and k = 0 (C = beta C)."""
+    import ctypes as C
+
+    import torch
+
+    from historymatching_b200 import _lib
+
+    rng = np.random.RandomState(7 * m + n + k)
+    ra, ca = (k, m) if tA else (m, k)
+    rb, cb = (n, k) if tB else (k, n)
+    bigA, bigB = rng.randn(ra + 3, ca + 6 + ca % 2), rng.randn(rb + 2, cb + 4 + cb % 2)  # even leading dimensions
+    assert bigA.shape[1] % 2 == 0 and bigB.shape[1] % 2 == 0
+    A, B = bigA[1:1 + ra, off:off + ca], bigB[2:2 + rb, off:off + cb]
+    Cm = rng.randn(m, n)
+    ref = 0.7 * (A.T if tA else A) @ (B.T if tB else B) - 0.3 * Cm
+    dA, dB, dC = (torch.as_tensor(x, device="cuda") for x in (bigA, bigB, Cm))
+    ctx = _lib.Context.get(0)
+    ctx.use_torch_stream()
+    pa = dA.data_ptr() + 8 * (bigA.shape[1] + off)
+    pb = dB.data_ptr() + 8 * (2 * bigB.shape[1] + off)
+    _lib.check(ctx.lib.hm_dgemm(ctx.handle, int(tA), int(tB), m, n, k, 0.7, C.c_void_p(pa), bigA.shape[1],
+                                C.c_void_p(pb), bigB.shape[1], -0.3, C.c_void_p(dC.data_ptr()), n))
+    np.testing.assert_allclose(dC.cpu().numpy(), ref, rtol=1e-12, atol=1e-12)
+
+
 def test_es_update_large_linear_gaussian_property():
     """BASELINE config-C shape (N=1024, M=16384, p=160): linearity in the innovations and
     agreement with the reference-order formula on a column subset."""
