@@ -35,6 +35,9 @@
 #include "hm_ptx.cuh"
 #include "hm_sim_common.cuh"
 
+// the sub-step lambda captures the patch registers (S, wx, wy) by reference before the first work item fills them
+#pragma nv_diag_suppress 549
+
 namespace hmsim {
 
 constexpr int kTbThreads = 512;
