@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     "A": dict(Nx=20, Ny=20, members=40, nTime=40, name="HistoryMatch.ipynb default: 20x20 grid, 40 members"),
+    "A200": dict(Nx=20, Ny=20, members=200, nTime=40, name="HistoryMatch.ipynb grid with a 200-member ensemble (BASELINE config 1)"),
     "C": dict(Nx=128, Ny=128, members=1024, nTime=40,
               name="ES-MDA pass, 128x128 synthetic permeability grid, 1024 members per GPU"),
     "D": dict(Nx=512, Ny=512, members=512, nTime=40,
@@ -375,6 +376,45 @@ def update_benchmarks(case, E0, Eo, noisy, pert, dec, cpu=True, reps=5):
     return out
 
 
+def cycle_benchmarks(case, E0, noisy, pert, dec, reps=3):
+    """Wall times of the complete iterative cycles of the notebook (BASELINE configs 1 and 2) at the bench ensemble
+    size, forward re-runs included: IES and ILES with ``xStep=0.4, iMax=10`` (HM:961, 1075-1077: 10 forward runs + 10
+    Gauss-Newton steps each; ILES with the bump taper of radius 1.2) and ES-MDA with ``Na = 4`` (4 forward runs + 4
+    updates).  Inputs resident on the device, CUDA events around the whole call."""
+    import torch
+
+    from historymatching_b200 import analysis as ha
+
+    dev = E0.device
+    N, M = E0.shape
+    g = case.grid
+    ix, iy = np.divmod(np.arange(M), g.Ny)
+    xy_prm = np.stack([(ix + 0.5) * g.Lx / g.Nx, (iy + 0.5) * g.Ly / g.Ny], 1)
+    xy_obs = np.tile(xy_prm[case.obs_cell], (case.nTime, 1))
+    taper = ha.bump_taper(torch.as_tensor(xy_prm, device=dev), torch.as_tensor(xy_obs, device=dev), 1.2)
+    fwd = lambda X: case.forward(X.contiguous())[0]  # noqa: E731
+    rng = np.random.RandomState(11)
+    Zs = [rng.randn(N, case.p) for _ in range(4)]
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    out = dict(N=N, M=M, p=case.p, nTime=case.nTime, forward_runs=dict(ies=10, iles=10, es_mda=4))
+    out["ies_ms"] = timed(lambda: ha.IES(E0, fwd, noisy, pert, dec, xStep=0.4, iMax=10))
+    out["iles_ms"] = timed(lambda: ha.ILES(E0, fwd, noisy, pert, dec, taper, xStep=0.4, iMax=10))
+    out["es_mda_ms"] = timed(lambda: ha.es_mda(E0, fwd, noisy, case.R12, [4.0] * 4, perturbs=Zs))
+    out["forward_ms"] = timed(lambda: fwd(E0))
+    return out
+
+
 # ---- GPU arm ------------------------------------------------------------------------------------
 def main():
     args = parse()
@@ -688,6 +728,9 @@ def measure(args, wl, rank, world, local_rank, dev, steps, warmup, full):
         line["e2e"] = e2e
     if world == 1 and not args.no_update_bench:
         line["update"] = update_benchmarks(case, E0, Eo, noisy, pert, dec, cpu=not args.no_cpu_baseline)
+    if world == 1 and full and wl["Nx"] * wl["Ny"] <= 4096 and not args.no_update_bench:
+        # the iterative cycles of the notebook incl. their forward re-runs (BASELINE configs 1, 2), undamped perturbations
+        line["cycles"] = cycle_benchmarks(case, E0, noisy, pert / np.sqrt(ALPHA), dec * np.sqrt(ALPHA))
     if world == 1 and full and wl["Nx"] * wl["Ny"] <= 4096 and not args.no_e2e:
         line["e2e_dropin"] = dropin_forward_bench(wl)  # the notebook-cell path (BASELINE configs 1, 2, 5)
     if not args.no_cpu_baseline and world == 1:
