@@ -329,3 +329,32 @@ def test_header_is_plain_c_and_matches_the_ctypes_mirrors(tmp_path):
     assert version >= 100
     assert rc in (0, -4)  # HM_OK on a GPU box, HM_ERR_NO_DEVICE here: never a silent CPU path
     assert size_desc == ctypes.sizeof(_lib.SimDesc) and size_stats == ctypes.sizeof(_lib.SimStats)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) prints ONE JSON line with the contract's
+    keys, the GPU arm's metric / unit / workload, and loads no CUDA code; the GPU arm's helpers agree on the workload text."""
+    import json
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "A", "--steps", "1",
+                          "--warmup", "0", "--cpu-seconds", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "member*steps/s" and d["higher_is_better"] is True
+    assert d["vs_baseline"] is None and d["dtype"] == "f64" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == dict(value=d["value"], unit=d["unit"], h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+    sys.path.insert(0, root)
+    import bench
+
+    wl = dict(bench.WORKLOADS["A"])
+    assert bench.workload_config(wl, 1)["workload"] == d["config"]["workload"]
+    assert set(bench.WORKLOADS) >= {"A", "A200", "C", "D"}
+    assert bench.WORKLOADS["C"]["members"] == 1024 and bench.WORKLOADS["D"]["Nx"] == 512
