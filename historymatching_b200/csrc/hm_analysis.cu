@@ -232,7 +232,7 @@ k_iles_step(int N, int64_t M, int p, double xStep, const double* __restrict__ S,
     double* A = sm;                 // N*N  : Wi -> Wi^-1 -> centred
     double* G = A + N * N;          // N*N
     double* Cc = G + N * N;         // N*N
-    double* Y0 = Cc + N * N;        // N*p (only the first n columns used, row pitch n)
+    double* Y0 = Cc + N * N;        // N*p: Y0 transposed, n rows (active observations) of pitch N
     double* c = Y0 + (size_t)N * p; // p
     double* colmean = c + p;        // N
     int* idx = (int*)(colmean + N); // p
@@ -331,58 +331,65 @@ k_iles_step(int N, int64_t M, int p, double xStep, const double* __restrict__ S,
     for (int i = wrp; i < N; i += nwarp)
         for (int j = lane; j < N; j += 32) A[i * N + j] -= colmean[j];
     __syncthreads();
-    // Y0 = A Si,  Si[k][a] = S[k][idx[a]] c[a]
+    // Y0 = A Si,  Si[k][a] = S[k][idx[a]] c[a]; kept TRANSPOSED (Y0t[a][r], row pitch N) so that the N^2 n loop below reads it
+    // with consecutive lanes on consecutive addresses (the [r][a] layout made every lane walk its own row: one 32-byte
+    // sector per lane and load - with the workspace in global memory that was most of the N = 200 step)
     for (int r = wrp; r < N; r += nwarp)
         for (int a = lane; a < n; a += 32) {
             double acc = 0.0;
             for (int k = 0; k < N; ++k) acc = fma(A[r * N + k], S[(int64_t)k * p + idx[a]], acc);
-            Y0[r * n + a] = acc * c[a];
+            Y0[a * N + r] = acc * c[a];
         }
     __syncthreads();
-    // G = Di Y0^T + (N-1)(I - Wi) ;  C = Y0 Y0^T + (N-1) I
+    // G = Di Y0^T + (N-1)(I - Wi), kept transposed (Gt[l][r]) for the solves ;  C = Y0 Y0^T + (N-1) I
     for (int r = wrp; r < N; r += nwarp)
         for (int l = lane; l < N; l += 32) {
             double g = 0.0, cc = 0.0;
             for (int a = 0; a < n; ++a) {
-                const double y = Y0[l * n + a];
+                const double y = Y0[a * N + l];
                 g = fma(D[(int64_t)r * p + idx[a]] * c[a], y, g);
-                cc = fma(Y0[r * n + a], y, cc);
+                cc = fma(Y0[a * N + r], y, cc);
             }
-            const int e = r * N + l;
-            G[e] = g + nm1 * ((r == l ? 1.0 : 0.0) - W[e]);
-            Cc[e] = cc + (r == l ? nm1 : 0.0);
+            G[l * N + r] = g + nm1 * ((r == l ? 1.0 : 0.0) - W[r * N + l]);
+            Cc[r * N + l] = cc + (r == l ? nm1 : 0.0);
         }
     __syncthreads();
-    // Cholesky of C (lower, in place)
+    // Cholesky of C (lower, in place); the scaled column k is also kept contiguous (colk) for the trailing update
+    double* colk = colmean;  // the column means are no longer needed
     for (int k = 0; k < N; ++k) {
         const double dkk = Cc[k * N + k];
         if (tid == 0 && !(dkk > 0.0)) s_fail = 1;
         const double d = sqrt(dkk);
         __syncthreads();
-        for (int a = k + tid; a < N; a += nt) Cc[a * N + k] = (a == k) ? d : Cc[a * N + k] / d;
+        for (int a = k + tid; a < N; a += nt) {
+            const double v = (a == k) ? d : Cc[a * N + k] / d;
+            Cc[a * N + k] = v;
+            colk[a] = v;
+        }
         __syncthreads();
         for (int a = k + 1 + wrp; a < N; a += nwarp) {
-            const double cak = Cc[a * N + k];
-            for (int b = k + 1 + lane; b <= a; b += 32) Cc[a * N + b] -= cak * Cc[b * N + k];
+            const double cak = colk[a];
+            for (int b = k + 1 + lane; b <= a; b += 32) Cc[a * N + b] -= cak * colk[b];
         }
         __syncthreads();
     }
-    // dW rows: solve C x = G[r,:]^T, one row per thread
+    // dW rows: solve C x = G[r,:]^T, one row r per thread = column r of Gt (consecutive threads on consecutive addresses)
     for (int r = tid; r < N; r += nt) {
-        double* g = G + r * N;
+        double* g = G + r;
         for (int k = 0; k < N; ++k) {
-            double v = g[k];
-            for (int a = 0; a < k; ++a) v -= Cc[k * N + a] * g[a];
-            g[k] = v / Cc[k * N + k];
+            double v = g[k * N];
+            for (int a = 0; a < k; ++a) v -= Cc[k * N + a] * g[a * N];
+            g[k * N] = v / Cc[k * N + k];
         }
         for (int k = N - 1; k >= 0; --k) {
-            double v = g[k];
-            for (int a = k + 1; a < N; ++a) v -= Cc[a * N + k] * g[a];
-            g[k] = v / Cc[k * N + k];
+            double v = g[k * N];
+            for (int a = k + 1; a < N; ++a) v -= Cc[a * N + k] * g[a * N];
+            g[k * N] = v / Cc[k * N + k];
         }
     }
     __syncthreads();
-    for (int e = tid; e < N * N; e += nt) W[e] = fma(xStep, G[e], W[e]);
+    for (int r = wrp; r < N; r += nwarp)
+        for (int l = lane; l < N; l += 32) W[r * N + l] = fma(xStep, G[l * N + r], W[r * N + l]);
     if (tid == 0 && s_fail) atomicExch(fail, 1);
     }
 }
