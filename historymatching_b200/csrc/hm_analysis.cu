@@ -218,7 +218,7 @@ k_local_analysis(int64_t M, int p, double nm1, const double* __restrict__ A,
 //   non-singular Wi), Y0 = center(Ai) Si, G = Di Y0^T + (N-1)(I - Wi), C = Y0 Y0^T + (N-1) I
 //   (= the inverse of the reference's SVD expression for covw), Cholesky of C, dW = G C^-1,
 //   Wi += xStep dW.  Si / Di are the tapered, active columns of S / D as in k_local_analysis.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024, 1)
 k_iles_step(int N, int64_t M, int p, double xStep, const double* __restrict__ S, const double* __restrict__ D,
             const double* __restrict__ taper, double* __restrict__ Ws, int* __restrict__ fail, double* gws,
             size_t gws_stride) {
@@ -655,15 +655,19 @@ extern "C" int hm_iles_step(hm_ctx* ctx, int64_t N, int64_t M, int64_t p, double
     HM_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), ctx->stream));
     double* gws = nullptr;
     size_t gstride = 0;
-    unsigned grid = (unsigned)M;
+    unsigned grid = (unsigned)M, block = 256;
     if (smem > kMaxWorkSmem) {  // 3 N^2 + N p doubles do not fit shared memory: global-memory workspace, persistent CTAs
         gstride = (smem / sizeof(double) + 15) & ~(size_t)15;
-        grid = (unsigned)std::min<int64_t>(M, (int64_t)ctx->sm_count * 4);
+        // 1024 threads, one resident CTA per SM: the N x N sweeps of a column step are spread over four times the threads
+        // and the resident matrices (148 x 3 N^2 doubles) stay in L2.  Measured at N = 200, M = 400, p = 160 (ms per step):
+        // 256 threads x 4 CTAs per SM 32.9, 512 x 2 26.1, 1024 x 1 (grid = SMs / 2 x SMs) 21.1 / 19.6
+        block = 1024;
+        grid = (unsigned)std::min<int64_t>(M, (int64_t)ctx->sm_count * 2);
         HM_CHECK(ctx->ws.get("an.loc_ws", gstride * grid, &gws));
         smem = 0;
     }
     HM_CUDA(cudaFuncSetAttribute(k_iles_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_iles_step<<<grid, 256, smem, ctx->stream>>>((int)N, M, (int)p, xStep, S, D, taper, Ws, fail, gws, gstride);
+    k_iles_step<<<grid, block, smem, ctx->stream>>>((int)N, M, (int)p, xStep, S, D, taper, Ws, fail, gws, gstride);
     ctx->launches += 1;
     HM_CUDA(cudaGetLastError());
     return check_info(ctx, fail, "localised IES step (singular Wi or non-SPD Gauss-Newton matrix)");
