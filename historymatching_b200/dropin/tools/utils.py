@@ -136,6 +136,12 @@ def _parallel_enabled():
     return bool(nCPU) and nCPU > 1
 
 
+def _inside_member():
+    from TPFA_ResSim import inside_member
+
+    return inside_member()
+
+
 def apply(fun, *args, pbar=True, **kwargs):
     """Apply ``fun`` along axis 0 of every positional and keyword argument.
 
@@ -165,7 +171,7 @@ def apply(fun, *args, pbar=True, **kwargs):
     else:
         pbar = progbar(disable=True)
 
-    if _parallel_enabled() and len(inputs) > 1:
+    if _parallel_enabled() and len(inputs) > 1 and not _inside_member():
         # NB: threads share memory, so a `fun.nCalls` counter is bumped by the calls
         # themselves (the reference adds len(inputs) only because child processes cannot).
         output = _batched_map(_fun, inputs, pbar)
@@ -181,48 +187,59 @@ def apply(fun, *args, pbar=True, **kwargs):
     return output
 
 
-_pool = None
-_pool_lock = threading.Lock()
+class _Member(threading.Thread):
+    """Persistent worker: one member of a chunk runs on it as a coroutine of ``TPFA_ResSim.Collector`` (creating 40
+    threads per ensemble run costs more than the 20 x 20 forward run itself).  The thread blocks on ``lock`` whenever it
+    does not hold the collector's baton; ``task`` is set by the dispatching thread before the baton first arrives."""
 
+    def __init__(self):
+        super().__init__(daemon=True, name="hm-member")
+        self.lock = threading.Lock()
+        self.lock.acquire()
+        self.task = None
+        self.start()
 
-def _member_pool():
-    """Persistent worker threads for the members of a batch (creating 40 threads per ensemble run costs more than the
-    20 x 20 forward run itself).  Every member of a chunk needs its own thread: a member blocks inside ``ResSim.sim``
-    until the whole chunk has arrived at the collector."""
-    global _pool
-    from concurrent.futures import ThreadPoolExecutor
-
-    with _pool_lock:
-        if _pool is None or _pool._max_workers < max_batch:
-            _pool = ThreadPoolExecutor(max_workers=max_batch, thread_name_prefix="hm-member")
-        return _pool
-
-
-def _batched_map(_fun, inputs, pbar):
-    """Run the members on threads; their ``ResSim.sim`` calls rendezvous into batched GPU runs."""
-    from TPFA_ResSim import Collector
-
-    output = [None] * len(inputs)
-    errors = [None] * len(inputs)
-    pool = _member_pool()
-    for lo in range(0, len(inputs), max_batch):
-        idx = range(lo, min(lo + max_batch, len(inputs)))
-        collector = Collector(len(idx))
-
-        def work(i):
-            collector.attach()
+    def run(self):
+        while True:
+            self.lock.acquire()  # the baton arrives: run this chunk's member
+            collector, me, work = self.task
+            self.task = None
+            collector.attach(me)
             try:
-                output[i] = _fun(inputs[i])
-            except BaseException as e:  # noqa: BLE001 - re-raised in the caller below
-                errors[i] = e
+                work(me)
             finally:
                 collector.detach()
                 collector.finish()
 
-        for f in [pool.submit(work, i) for i in idx]:
-            f.result()
-            pbar.update()
-        for e in errors:
-            if e is not None:
-                raise e
+
+_members = []
+_members_lock = threading.Lock()  # one chunk at a time uses the workers
+
+
+def _batched_map(_fun, inputs, pbar):
+    """Run the members as coroutines on worker threads; their ``ResSim.sim`` calls rendezvous into batched GPU runs."""
+    from TPFA_ResSim import Collector
+
+    output = [None] * len(inputs)
+    errors = [None] * len(inputs)
+    with _members_lock:
+        for lo in range(0, len(inputs), max_batch):
+            n = min(max_batch, len(inputs) - lo)
+            while len(_members) < n:
+                _members.append(_Member())
+
+            def work(me, lo=lo):
+                try:
+                    output[lo + me] = _fun(inputs[lo + me])
+                except BaseException as e:  # noqa: BLE001 - re-raised in the caller below
+                    errors[lo + me] = e
+                pbar.update()
+
+            collector = Collector([m.lock for m in _members[:n]])
+            for me in range(n):
+                _members[me].task = (collector, me, work)
+            collector.run()
+            for e in errors:
+                if e is not None:
+                    raise e
     return output

@@ -358,3 +358,64 @@ def test_bench_reference_arm_contract():
     assert bench.workload_config(wl, 1)["workload"] == d["config"]["workload"]
     assert set(bench.WORKLOADS) >= {"A", "A200", "C", "D"}
     assert bench.WORKLOADS["C"]["members"] == 1024 and bench.WORKLOADS["D"]["Nx"] == 512
+
+
+def test_collector_scheduling_edge_cases(monkeypatch):
+    """The baton scheduler behind apply(): members that call sim() several times (one batch per round), chunks of
+    `max_batch` members, a nested apply() inside a member (runs in place, no second rendezvous), exceptions, and the
+    order of the members' side effects (one member runs at a time, in input order, up to its first sim())."""
+    batches, trace = [], []
+
+    def fake_run(reqs):
+        batches.append(len(reqs))
+        for r in reqs:
+            r.result = np.tile(r.S0, (r.nSteps + 1, 1)) + r.K[0].mean()
+            r.done = True
+
+    monkeypatch.setattr(simulator, "run_requests", fake_run)
+    model = simulator.ResSim(Nx=4, Ny=4, Lx=1, Ly=1)
+    model.inj_xy, model.prd_xy, model.inj_rates, model.prd_rates = [[0.1, 0.1]], [[0.9, 0.9]], [[1]], [[1]]
+
+    def two_runs(k):
+        trace.append(("start", k))
+        m = copy.deepcopy(model)
+        m.K = np.full(16, k)
+        a = m.sim(0.1, 1, np.zeros(16), pbar=False)[-1, 0]
+        trace.append(("mid", k))
+        if k % 2:  # odd members run a second simulation from the first one's result
+            a = m.sim(0.1, 1, np.full(16, a), pbar=False)[-1, 0]
+        return a
+
+    utils.nCPU = "auto"
+    ks = np.arange(1.0, 7.0)
+    out = utils.apply(two_runs, ks, pbar=False)
+    assert out == [2.0, 2.0, 6.0, 4.0, 10.0, 6.0]
+    assert batches == [6, 3]                                     # all members, then the odd ones
+    assert trace[:6] == [("start", k) for k in ks]               # in input order, each up to its first sim()
+    assert [t for t in trace[6:]] == [("mid", k) for k in ks]    # and resumed in the same order
+
+    monkeypatch.setattr(utils, "max_batch", 4)                   # chunks of 4 members
+    batches.clear()
+    out = utils.apply(two_runs, np.arange(2.0, 22.0, 2.0), pbar=False)
+    assert batches == [4, 4, 2] and out == list(np.arange(2.0, 22.0, 2.0))
+    monkeypatch.setattr(utils, "max_batch", 512)
+
+    def nested(k):  # a member that maps over sub-cases itself: the inner apply runs in place on the member's thread
+        inner = utils.apply(lambda j: two_runs(2.0 * j), np.arange(1.0, 4.0), pbar=False)
+        return k + sum(inner)
+
+    batches.clear()
+    out = utils.apply(nested, np.arange(3.0), pbar=False)
+    assert out == [12.0, 13.0, 14.0]
+    assert batches == [3, 3, 3]                                  # the outer members' inner calls still rendezvous
+
+    def failing(k):
+        if k == 2:
+            raise KeyError("member 2")
+        return two_runs(k)
+
+    with pytest.raises(KeyError):
+        utils.apply(failing, np.arange(1.0, 5.0), pbar=False)
+    batches.clear()
+    assert utils.apply(two_runs, np.array([4.0, 8.0]), pbar=False) == [4.0, 8.0]  # the workers are reusable after an error
+    utils.nCPU = 1
