@@ -546,6 +546,7 @@ def measure(args, wl, rank, world, local_rank, dev, steps, warmup, full):
     ev0.record()
     phase = dict(setup=0.0, cg=0.0, flux=0.0, saturation=0.0, obs=0.0)
     upd_ms, fwd_ms, cg_member_iters, sat_member_substeps = 0.0, 0.0, 0, 0
+    upd_steps = []
     stats_acc = dict(cg_kernel_launches=0, sat_kernel_launches=0, mg_fp64_fallbacks=0, kernel_launches=0, sat_cell_updates=0)
     torch.cuda.nvtx.range_push("timed")  # lets ncu select the timed region (--nvtx --nvtx-include "timed/")
     for _ in range(args.steps):
@@ -554,7 +555,8 @@ def measure(args, wl, rank, world, local_rank, dev, steps, warmup, full):
         res = last["res"]
         for k in phase:
             phase[k] += res.stats["phase_ms"][k]
-        upd_ms += last["upd"][0].elapsed_time(last["upd"][1])
+        upd_steps.append(last["upd"][0].elapsed_time(last["upd"][1]))
+        upd_ms += upd_steps[-1]
         fwd_ms += last["fwd0"].elapsed_time(last["upd"][0])
         cg_member_iters += int(res.cg_iters.sum())
         sat_member_substeps += int(res.substeps.sum())
@@ -717,7 +719,7 @@ def measure(args, wl, rank, world, local_rank, dev, steps, warmup, full):
         steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
         vs_baseline=None, dtype="f64", data="synthetic",
         config=workload_config(wl, world), lanes_per_gpu=lanes_used,
-        update_ms=upd_ms / args.steps, forward_ms=fwd_ms / args.steps,
+        update_ms=upd_ms / args.steps, update_ms_steps=[round(u, 3) for u in upd_steps], forward_ms=fwd_ms / args.steps,
         phases_ms_per_step={k: v / attr_steps for k, v in phase.items()}, attribution=attribution,
         secondary_kernel=dict(kernel=other, achieved=(ob / (ot * 1e-3) / 1e9 if ot > 0 else 0.0), unit="GB/s"),
         members_failed=bad, gpu_launches=int(launches), clocks=sampler.summary(), roofline=roofline,
