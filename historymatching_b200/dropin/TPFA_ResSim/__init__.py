@@ -71,7 +71,9 @@ class ResSim(Grid2D, Plot2D):
         new = object.__new__(type(self))
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if isinstance(v, np.ndarray):
+            if k == "_sched":  # the cached well schedule: read-only arrays, shared
+                pass
+            elif isinstance(v, np.ndarray):
                 v = v.copy()
             elif isinstance(v, dict) and all(isinstance(x, np.ndarray) for x in v.values()):
                 v = {kk: x.copy() for kk, x in v.items()}
@@ -92,7 +94,17 @@ class ResSim(Grid2D, Plot2D):
 
     # ---- request assembly ------------------------------------------------------------
     def _schedule(self, nSteps):
-        """Signed well rates (nSteps, nW) and cells (nW,); validates the balance."""
+        """Signed well rates (nSteps, nW) and cells (nW,); validates the balance.
+
+        The members of an ensemble are deep copies of one model with the same wells, so the result is cached on the
+        instance (and travels with ``copy.deepcopy``); the key holds the bytes of the four small well arrays, so a
+        change made in place (``model.inj_rates[0] = 2``) is seen as well as an assignment."""
+        key = (nSteps, self.inj_xy.tobytes(), self.prd_xy.tobytes(), self.inj_rates.tobytes(), self.prd_rates.tobytes(),
+               self.inj_rates.shape, self.prd_rates.shape)
+        cached = self.__dict__.get("_sched")
+        if cached is not None and cached[0] == key:
+            self.actual_rates = {k: v.copy() for k, v in cached[3].items()}
+            return cached[1], cached[2]
         rates = []
         for kind, sign in (("inj", 1.0), ("prd", -1.0)):
             xy, r = getattr(self, f"{kind}_xy"), getattr(self, f"{kind}_rates")
@@ -107,7 +119,11 @@ class ResSim(Grid2D, Plot2D):
             raise ValueError("total injection must equal total production at every time step")
         cells = np.concatenate([self._inj_cells, self._prd_cells])  # collocated when the wells were set
         self.actual_rates = {"inj": np.array(rates[0]), "prd": -np.array(rates[1])}
-        return np.ascontiguousarray(q), cells
+        q = np.ascontiguousarray(q)
+        q.setflags(write=False)
+        cells.setflags(write=False)
+        object.__setattr__(self, "_sched", (key, q, cells, {k: v.copy() for k, v in self.actual_rates.items()}))
+        return q, cells
 
     def sim(self, dt, nSteps, S0, pbar=True, leave=False):
         """Run ``nSteps`` steps of length ``dt`` from saturation ``S0``.

@@ -419,3 +419,27 @@ def test_collector_scheduling_edge_cases(monkeypatch):
     batches.clear()
     assert utils.apply(two_runs, np.array([4.0, 8.0]), pbar=False) == [4.0, 8.0]  # the workers are reusable after an error
     utils.nCPU = 1
+
+
+def test_well_schedule_cache_sees_in_place_changes():
+    """ResSim caches the (validated) well schedule per instance and shares it with deep copies; assignments AND in-place
+    edits of the well arrays invalidate it."""
+    model = simulator.ResSim(Nx=4, Ny=4, Lx=1, Ly=1)
+    model.inj_xy, model.prd_xy = [[0.1, 0.1]], [[0.9, 0.9], [0.1, 0.9]]
+    model.inj_rates, model.prd_rates = [[1.0]], [[0.5], [0.5]]
+    q0, c0 = model._schedule(3)
+    assert q0.shape == (3, 3) and np.allclose(q0[0], [1, -0.5, -0.5]) and list(c0) == list(model.xy2ind(*np.array([[0.1, 0.1], [0.9, 0.9], [0.1, 0.9]]).T))
+    twin = copy.deepcopy(model)
+    q1, _ = twin._schedule(3)
+    assert q1 is q0 and not q0.flags.writeable                      # shared, read-only
+    assert twin._schedule(2)[0].shape == (2, 3)                     # another step count: rebuilt
+    twin.inj_rates[0] = 2.0                                         # in place: unbalanced now
+    with pytest.raises(ValueError):
+        twin._schedule(3)
+    twin.prd_rates[:] = 1.0
+    assert np.allclose(twin._schedule(3)[0][0], [2, -1, -1]) and np.allclose(twin.actual_rates["inj"], 2.0)
+    assert np.allclose(model._schedule(3)[0][0], [1, -0.5, -0.5])   # the original is untouched
+    twin.prd_xy = [[0.9, 0.1], [0.1, 0.9]]                          # assignment: new cells
+    assert list(twin._schedule(3)[1]) != list(c0)
+    model.actual_rates["inj"][:] = 7.0                              # the user's copy is theirs to edit
+    assert np.allclose(copy.deepcopy(model)._schedule(3)[0][0], [1, -0.5, -0.5])
