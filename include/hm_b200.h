@@ -175,9 +175,10 @@ int hm_dgemm(hm_ctx* ctx, int transA, int transB, int64_t m, int64_t n, int64_t 
  * ES analysis.  Replaces ens_update0 (HistoryMatch.py:578-586):
  *   E + D pinv(S^T S + (N-1) I) S^T X,  S = center(Eo) decorr,
  *   D = (obs - Eo - perturbs) decorr,  X = center(E).
- * E (N,M) is updated in place for the column range [col0, col0+ncols) it
- * holds (parameter-sharded multi-GPU use passes its own column block; Eo,
- * perturbs are always the full (N,p) blocks).  ldE = row stride of E.
+ * E (N,M) is updated in place; the M columns (parameters) are independent, so a
+ * parameter-sharded multi-GPU caller passes its own column block as E with M =
+ * the number of columns it holds (Eo, perturbs are always the full (N,p)
+ * blocks).  ldE = row stride of E.
  * ------------------------------------------------------------------------- */
 int hm_es_update(hm_ctx* ctx, int64_t N, int64_t M, int64_t p, double* E, int64_t ldE,
                  const double* Eo, const double* obs, const double* perturbs,
