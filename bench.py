@@ -537,14 +537,17 @@ def measure(args, wl, rank, world, local_rank, dev, steps, warmup, full):
     # must not land inside a timed region that may itself be only milliseconds long (workload A)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    post = Eo = None
+    post = Eo = res = None
     for _ in range(args.warmup):
-        # same assignment as in the timed loop: the previous pass's posterior stays referenced while the next one is
-        # computed, so the allocator's second 134 MB block is created here and not in the second timed pass
+        # the same references as in the timed loop: the previous pass's posterior AND its SimResult (`res`) stay alive
+        # while the next pass runs, so torch's caching allocator reaches its steady state here - otherwise the second
+        # timed pass is the first one whose update cannot reuse the freed result block and pays two cudaMalloc
+        # (0.7 - 75 ms inside update_ms; found with HM_BENCH_LOG=1)
         post, Eo = one_pass(E0)
         torch.cuda.synchronize()
+        res = last["res"]
         # the bookkeeping reductions of the timed loop too: their first call loads a torch kernel module (tens of ms)
-        int(last["res"].cg_iters.sum()), int(last["res"].substeps.sum())
+        int(res.cg_iters.sum()), int(res.substeps.sum())
         log("warm-up pass done")
     barrier()
     t_region0 = time.perf_counter()
