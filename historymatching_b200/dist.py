@@ -24,7 +24,10 @@ Product API of the sharded cycle (the loop the reference writes in its cells,
 * ``ies_sharded``      - iterative smoother: the ``N x N`` weight matrix ``W`` is
   replicated (every rank takes the same Gauss-Newton step from the gathered
   predicted data), the recomposition ``E = x0 + W X0`` runs on this rank's
-  parameter columns, the all-to-all returns member rows for the next forward run.
+  parameter columns, the all-to-all returns member rows for the next forward run;
+* ``iles_sharded``     - localised iterative smoother: the per-parameter weight matrices live
+  on this rank's parameter columns, step and recomposition are local
+  (``HistoryMatch.py:1007-1064``).
 """
 
 from __future__ import annotations
@@ -291,4 +294,50 @@ def ies_sharded(forward, E_local, N, obs, perturbs, decorr, xStep=1.0, iMax=4):
         ctx.use_torch_stream()
         _lib.check(ctx.lib.hm_ies_step(ctx.handle, N, p, ptr(W), ptr(Eo.contiguous()), ptr(y), ptr(pert), ptr(dec),
                                        float(xStep)))
+    return E, stats
+
+
+def iles_sharded(forward, E_local, N, obs, perturbs, decorr, taper_cols, xStep=1.0, iMax=4):
+    """Localised iterative ensemble smoother (``HistoryMatch.py:1007-1064``) of a member-sharded ensemble.
+
+    The per-parameter weight matrices ``Ws (m_loc, N, N)``, the anomalies and the mean live on this rank's parameter
+    columns (``taper_cols`` = the ``(m_loc, p)`` taper rows of those columns), where the batched Gauss-Newton step
+    (``hm_iles_step``) and the recomposition (``hm_iles_recompose``) are fully local; per iteration the predicted data
+    are all-gathered and one all-to-all returns member rows for the forward run.
+    Returns ``(E_local, stats)``; ``stats["Eo"]`` holds the gathered predicted data ``(N,p)`` of every iteration.
+    """
+    from . import _lib
+
+    dev = E_local.device
+    M = E_local.shape[1]
+    if dev.type != "cuda":
+        raise _lib.HmError("iles_sharded runs on CUDA tensors (no CPU fallback)")
+    y, pert, dec, tap = (_f64_on(x, dev).contiguous() for x in (obs, perturbs, decorr, taper_cols))
+    p = y.shape[0]
+    ctx = _lib.Context.get(dev.index if dev.index is not None else torch.cuda.current_device())
+    ctx.use_torch_stream()
+    rs = Resharder.get(N, M, dev)
+    E_cols = members_to_columns(E_local.contiguous(), N).contiguous()
+    m_loc = E_cols.shape[1]
+    if tuple(tap.shape) != (m_loc, p):
+        raise ValueError(f"taper_cols must be ({m_loc}, {p}): the taper rows of this rank's parameter columns")
+    X0 = torch.empty((N, m_loc), dtype=torch.float64, device=dev)
+    x0 = torch.empty(m_loc, dtype=torch.float64, device=dev)
+    ptr = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    _lib.check(ctx.lib.hm_center(ctx.handle, N, m_loc, ptr(E_cols), m_loc, ptr(X0), m_loc, ptr(x0), 0))
+    Ws = torch.eye(N, dtype=torch.float64, device=dev).repeat(m_loc, 1, 1).contiguous()
+    stats = dict(Eo=[])
+    E = E_local
+    for it in range(iMax + 1):
+        Ec = torch.empty((N, m_loc), dtype=torch.float64, device=dev)
+        ctx.use_torch_stream()
+        _lib.check(ctx.lib.hm_iles_recompose(ctx.handle, N, m_loc, ptr(Ws), ptr(X0), ptr(x0), ptr(Ec)))
+        E = rs.to_members(Ec) if rs.size > 1 else Ec
+        if it == iMax:
+            break
+        Eo = gather_members(forward(E), N).contiguous()
+        stats["Eo"].append(Eo)
+        ctx.use_torch_stream()
+        _lib.check(ctx.lib.hm_iles_step(ctx.handle, N, m_loc, p, ptr(Ws), ptr(Eo), ptr(y), ptr(pert), ptr(dec), ptr(tap),
+                                        float(xStep)))
     return E, stats

@@ -66,8 +66,12 @@ def _worker(rank, size, port, out):
     post_ies, st = hd.ies_sharded(fwd_loc, E[lo:hi].contiguous(), N, obs, pert, dec, xStep=0.6, iMax=3)
     ref_ies, _ = ha.IES(E, lambda X: case.forward(X)[0], obs, pert, dec, xStep=0.6, iMax=3)
     ok_ies = torch.allclose(post_ies, ref_ies[lo:hi], rtol=1e-8, atol=1e-10) and len(st["Eo"]) == 3
+    post_iles, st = hd.iles_sharded(fwd_loc, E[lo:hi].contiguous(), N, obs, pert, dec, taper[clo:chi].contiguous(),
+                                    xStep=0.6, iMax=2)
+    ref_iles, _ = ha.ILES(E, lambda X: case.forward(X)[0], obs, pert, dec, taper, xStep=0.6, iMax=2)
+    ok_iles = torch.allclose(post_iles, ref_iles[lo:hi], rtol=1e-8, atol=1e-10) and len(st["Eo"]) == 2
     with open(os.path.join(out, f"rank{rank}"), "w") as f:
-        f.write(f"{int(ok)}{int(ok_mda)}{int(ok_ies)}")
+        f.write(f"{int(ok)}{int(ok_mda)}{int(ok_ies)}{int(ok_iles)}")
     dist.destroy_process_group()
 
 
@@ -78,4 +82,33 @@ def test_sharded_forward_and_update_world2_nccl(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
-    assert [open(tmp_path / f"rank{r}").read() for r in range(2)] == ["111", "111"]  # update, ES-MDA, IES
+    assert [open(tmp_path / f"rank{r}").read() for r in range(2)] == ["1111", "1111"]  # update, ES-MDA, IES, ILES
+
+
+def test_sharded_cycles_single_process_equal_the_unsharded_functions():
+    """Without a process group the sharded cycles are the single-device functions (world size 1: no exchange)."""
+    import torch
+
+    from historymatching_b200 import analysis as ha
+    from historymatching_b200 import dist as hd
+    from historymatching_b200.workflow import HistoryMatchCase
+
+    case = HistoryMatchCase(20, 20, 2.0, 1.0, 0.025, 5)
+    N, M, p = 12, case.grid.M, case.p
+    rng = np.random.RandomState(5)
+    dev = torch.device("cuda")
+    E = torch.as_tensor(np.clip(rng.randn(N, M), -2, 2) * 0.3, device=dev)
+    obs = torch.as_tensor(rng.rand(p) * 0.3, device=dev)
+    pert = torch.as_tensor(rng.randn(N, p) @ case.R12.T, device=dev)
+    dec = torch.as_tensor(case.decorr, device=dev)
+    taper = torch.as_tensor(rng.rand(M, p), device=dev)
+    fwd = lambda X: case.forward(X.contiguous())[0]  # noqa: E731
+    post, st = hd.iles_sharded(fwd, E, N, obs, pert, dec, taper, xStep=0.5, iMax=2)
+    ref, st_ref = ha.ILES(E, fwd, obs, pert, dec, taper, xStep=0.5, iMax=2)
+    assert torch.allclose(post, ref, rtol=1e-10, atol=1e-12) and len(st["Eo"]) == 2
+    assert torch.allclose(st["Eo"][1], st_ref.Eo[1], rtol=1e-10, atol=1e-12)
+    post, st = hd.ies_sharded(fwd, E, N, obs, pert, dec, xStep=0.5, iMax=2)
+    ref, _ = ha.IES(E, fwd, obs, pert, dec, xStep=0.5, iMax=2)
+    assert torch.allclose(post, ref, rtol=1e-10, atol=1e-12) and len(st["Eo"]) == 2
+    with pytest.raises(ValueError):
+        hd.iles_sharded(fwd, E, N, obs, pert, dec, taper[:10], iMax=1)
