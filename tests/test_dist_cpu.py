@@ -92,3 +92,18 @@ def test_single_process_is_identity():
     E = torch.randn(4, 6, dtype=torch.float64)
     assert hd.members_to_columns(E, 4) is E and hd.columns_to_members(E, 4, 6) is E
     assert hd.member_slice(10, 1, 3) == (4, 7) and hd.member_slice(10, 2, 3) == (7, 10)
+
+
+def test_block_partitions_cover_without_overlap():
+    """member_slice / column_slice: contiguous blocks in rank order, sizes differing by at most one, also when there are
+    fewer items than ranks (empty blocks at the end)."""
+    from historymatching_b200 import dist as hd
+
+    for size in range(1, 9):
+        for n in range(0, 40):
+            blocks = [hd.member_slice(n, r, size) for r in range(size)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+            lens = [hi - lo for lo, hi in blocks]
+            assert max(lens) - min(lens) <= 1 and lens == sorted(lens, reverse=True)
+            assert blocks == [hd.column_slice(n, r, size) for r in range(size)]
