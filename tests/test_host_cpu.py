@@ -443,3 +443,36 @@ def test_well_schedule_cache_sees_in_place_changes():
     assert list(twin._schedule(3)[1]) != list(c0)
     model.actual_rates["inj"][:] = 7.0                              # the user's copy is theirs to edit
     assert np.allclose(copy.deepcopy(model)._schedule(3)[0][0], [1, -0.5, -0.5])
+
+
+def test_robust_increments_host_logic():
+    """enopt_fast.robust_increments against the formulas of ens_eval_duplex (Optimise.py:833-853) with a stand-in
+    objective: what is paired with what, ONE batch per call (2 nEns members for StoSAG), the mean model."""
+    from historymatching_b200.enopt_fast import robust_increments
+
+    rng = np.random.RandomState(2)
+    n, du, dx = 5, 2, 7
+    U, X, u = rng.randn(n, du), rng.randn(n, dx), rng.randn(du)
+    calls = []
+
+    def obj_ux(uu, xx):  # a scalar objective of (control, uncertain parameter)
+        return float(np.sin(uu).sum() * np.cos(xx).sum() + uu[0] * xx[1])
+
+    def npv_batch(params):
+        calls.append(len(params))
+        assert all(set(q) == {"inj_xy", "K"} for q in params)
+        return np.array([obj_ux(q["inj_xy"], q["K"]) for q in params])
+
+    paired = robust_increments(npv_batch, "Paired", u, U, X)
+    np.testing.assert_allclose(paired, [obj_ux(U[i], X[i]) for i in range(n)])
+    stosag = robust_increments(npv_batch, "StoSAG", u, U, X)
+    np.testing.assert_allclose(stosag, [obj_ux(U[i], X[i]) - obj_ux(u, X[i]) for i in range(n)])
+    x1 = X.mean(0)
+    for kind in ("Mean-model", "Fragile"):
+        np.testing.assert_allclose(robust_increments(npv_batch, kind, u, U, X), [obj_ux(U[i], x1) for i in range(n)])
+    assert calls == [n, 2 * n, n, n]
+    with pytest.raises(ValueError):
+        robust_increments(npv_batch, "Regular", u, U, X)
+    other = robust_increments(lambda ps: np.array([q["rates"].sum() + q["perm"].sum() for q in ps]), "Paired", u, U, X,
+                              param_u="rates", param_x="perm")
+    np.testing.assert_allclose(other, U.sum(1) + X.sum(1))
